@@ -89,13 +89,13 @@ struct Lsodes {
   bool analysed = false;
   // state corresponding to COMMON /DLS001/, /DLSS01/
   double CONIT, CRATE, EL[14], ELCO[14][13], HOLD, RMAX, TESCO[4][13];
-  double CCMAX, EL0, H, HMIN, HMXI, HU, RC, TN, UROUND;
+  double CCMAX, EL0, H, HMIN, HMXI, HU = 0, RC, TN, UROUND;
   int INIT = 0, MXSTEP, MXHNIL, NHNIL, NSLAST, NYH;
   int IALTH, IPUP, LMAX, MEO, NQNYH, NSLP;
   int ICF, IERPJ, IERSL, JCUR, JSTART, KFLAG, L;
-  int METH, MITER, MAXORD, MAXCOR, MSBP, MXNCF, N, NQ, NST, NFE, NJE, NQU;
+  int METH, MITER, MAXORD, MAXCOR, MSBP, MXNCF, N, NQ = 0, NST = 0, NFE = 0, NJE = 0, NQU = 0;
   double CON0, CONMIN, CCMXJ, PSMALL, RBIG;
-  int MSBJ, NSLJ, NLU, IMXER = 0, iplost = 0;
+  int MSBJ, NSLJ, NLU = 0, IMXER = 0, iplost = 0;
   double Padd = 0.0;   // value of P on the diagonals DPREP appends to the user's pattern
   long n_solve = 0, n_cfail = 0, n_efail = 0;
   bool IHIT = false;
