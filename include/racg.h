@@ -1,0 +1,170 @@
+/*
+ * racg.h -- C-ABI of libracg.so: the B200 (sm_100a) replacement for RAC-2D's
+ * per-cell stiff-chemistry solve.
+ *
+ * The reference has no FFI seam; the cut is the zero-argument
+ *     call chem_evol_solve              (reference src/disk.f90:1686)
+ * inside calc_this_cell (src/disk.f90:1629-1801), whose inputs/outputs are the
+ * module globals of src/chemistry.f90:158-170 and whose only callees are DLSODES
+ * (src/opkdmain.f:1756) with the callbacks chem_ode_f / chem_ode_jac
+ * (src/disk.f90:4569, 4746).  This header declares what a Fortran host binds with
+ * ISO_C_BINDING instead (see INTEGRATION.md for the interface module).
+ *
+ * Conventions: every array is caller-owned, column-major as Fortran lays it out,
+ * index VALUES are 1-based exactly as in the reference tables; scalars by value.
+ * Every function returns 0 on success and a negative code on error (never
+ * aborts, never falls back to a CPU path); racg_last_error() gives the text.
+ * A handle is bound to the CUDA device current at creation; use one handle per
+ * host thread / per GPU.
+ */
+#ifndef RACG_H
+#define RACG_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RACG_NPAR 32     /* doubles per cell record (enum racg_par) */
+#define RACG_NSTAT 16    /* doubles per cell in stats */
+#define RACG_NAME_LEN 12 /* const_len_species_name, src/chemistry.f90:11 */
+#define RACG_NELEM 20    /* const_nElement, src/chemistry.f90:20 */
+
+/* error codes */
+#define RACG_OK 0
+#define RACG_ERR_ARG (-1)
+#define RACG_ERR_CUDA (-2)
+#define RACG_ERR_NETWORK (-3)   /* what the reference turns into error_stop */
+#define RACG_ERR_UNSUPPORTED (-4)
+
+/* Columns of cellpar(ncell, RACG_NPAR): the fields of type_cell_rz_phy_basic
+ * (src/data_struct.f90:316-442) that chem_cal_rates (src/chemistry.f90:591-966),
+ * chem_ode_f/jac and chem_set_solver_flags_alt read.  0-based. */
+enum racg_par {
+  RACG_P_Tgas = 0, RACG_P_Tdust, RACG_P_n_gas, RACG_P_GrainRadius_CGS,
+  RACG_P_sigdust_ave, RACG_P_ndust_tot, RACG_P_ratioDust2HnucNum,
+  RACG_P_SitesPerGrain, RACG_P_zeta_cosmicray_H2, RACG_P_zeta_Xray_H2,
+  RACG_P_Ncol_toISM, RACG_P_omega_albedo, RACG_P_G0_UV_toISM,
+  RACG_P_G0_UV_toStar, RACG_P_G0_UV_H2phd, RACG_P_G0_UV_toStar_photoDesorb,
+  RACG_P_Av_toISM, RACG_P_Av_toStar, RACG_P_phflux_Lya,
+  RACG_P_fss_toISM_H2, RACG_P_fss_toISM_CO, RACG_P_fss_toISM_H2O,
+  RACG_P_fss_toISM_OH, RACG_P_fss_toStar_H2, RACG_P_fss_toStar_CO,
+  RACG_P_fss_toStar_H2O, RACG_P_fss_toStar_OH, RACG_P_COUNT
+};
+
+/* The scalars of chemsol_params (src/chemistry.f90:107-135) and of phy_const
+ * (src/sub_global_variables.f90) the path uses.  The Fortran host fills the
+ * constants from its own modules so that the reference's digits are used
+ * (SURVEY App. F.7); racg_default_cfg() fills the same values. */
+typedef struct racg_cfg {
+  double Diff2DesorRatio;               /* chemsol_params, default 0.5 */
+  double special_gH_E_diff;             /* 225 */
+  int H2_form_use_moeq;                 /* only 0 supported */
+  int use_special_gH_mobi;              /* 0 / 1 */
+  int update_gH_params_realtime;        /* only 0 supported */
+  int evol_dust_size;                   /* only 0 supported */
+  double phy_Pi, phy_elementaryCharge_SI, phy_CoulombConst_SI, phy_mProton_CGS,
+         phy_kBoltzmann_SI, phy_kBoltzmann_CGS, phy_hbarPlanck_CGS,
+         phy_SecondsPerYear, phy_Habing_photon_flux_CGS, phy_UVext2Av,
+         const_cosmicray_attenuate_N, const_cosmicRay_intensity_0,
+         CosmicDesorpPreFactor, CosmicDesorpGrainT;
+} racg_cfg;
+
+typedef struct racg_handle racg_handle;
+
+const char* racg_last_error(void);
+void racg_default_cfg(racg_cfg* cfg);
+/* selects the CUDA device for subsequent racg_network_create calls of this thread */
+int racg_set_device(int device);
+
+/* Replaces the once-per-run setup chem_make_sparse_structure +
+ * chem_prepare_solver_storage + DLSODES' DIPREP/DPREP (src/chemistry.f90:1858-1885,
+ * 1943-1973; src/opkda1.f:1210-1540): takes the already-parsed tables of
+ * type_chemical_evol_reactions / _species (src/chemistry.f90:72-104) from the
+ * Fortran loaders, packs them into SoA device arrays, builds IA/JA, computes a
+ * fill-reducing ordering and the symbolic LU every cell shares, uploads.
+ *   reac(3,R), prod(4,R)       int, 1-based species ids, 0 = empty
+ *   n_reac(R), n_prod(R), itype(R)
+ *   ABC(3,R), T_range(2,R)
+ *   ctype(2,R)                 character(len=2) ctype(R)
+ *   names(12,N)                character(len=12) names(N), blank padded
+ *   elements(20,N), mass_num(N), vib_freq(N), Edesorb(N)
+ *   dupli_ptr(R+1) 0-based offsets into dupli_list(*) (1-based reaction ids):
+ *                              chem_net%dupli(i)%list flattened */
+int racg_network_create(racg_handle** h, int R, int N, const int* reac, const int* prod,
+                        const int* n_reac, const int* n_prod, const int* itype,
+                        const double* ABC, const double* T_range, const char* ctype,
+                        const char* names, const int* elements, const double* mass_num,
+                        const double* vib_freq, const double* Edesorb, const int* dupli_ptr,
+                        const int* dupli_list, const racg_cfg* cfg);
+int racg_destroy(racg_handle* h);
+
+/* sizes[0..7] = R, N, NEQ, NNZ (= chemsol_params%NNZ), NNZ after DPREP's diagonals,
+ * nnz(L+D+U) of the shared symbolic factorisation (species block), dense-tail size,
+ * number of factorisation levels */
+int racg_network_sizes(const racg_handle* h, int* sizes);
+/* IA(NEQ+1), JA(NNZ) exactly as chem_prepare_solver_storage stores them in
+ * IWORK(31:31+NEQ) and IWORK(32+NEQ:31+NEQ+NNZ) (src/chemistry.f90:1962-1971):
+ * 1-based, column-major, rows ascending, without DPREP's added diagonals. */
+int racg_network_pattern(const racg_handle* h, int* ia, int* ja);
+/* the elimination order (perm(N), 1-based species ids, first eliminated first) */
+int racg_network_ordering(const racg_handle* h, int* perm);
+
+/* K1: chem_cal_rates for a batch.  cellpar(ncell,NPAR) -> rates(ncell,R) [yr^-1] */
+int racg_rates(racg_handle* h, int ncell, const double* cellpar, double* rates);
+/* K2/K3: chem_ode_f and the whole chem_ode_jac matrix for a batch.
+ * y(ncell,NEQ), rates(ncell,R) -> ydot(ncell,NEQ), pd(ncell,NNZ) in the slot order
+ * of racg_network_pattern.  ydot or pd may be NULL. */
+int racg_rhs_jac(racg_handle* h, int ncell, const double* cellpar, const double* y,
+                 const double* rates, double* ydot, double* pd);
+
+/* chem_set_solver_flags_alt(j) (src/chemistry.f90:205-268) for a batch:
+ * rtol(ncell,NEQ), atol(ncell,NEQ) */
+int racg_solver_flags_alt(const racg_handle* h, int j, double RTOL, double ATOL, int ncell,
+                          const double* cellpar, double* rtol, double* atol);
+
+typedef struct racg_solve_params {
+  double ratio_tstep;        /* chemsol_params%ratio_tstep */
+  int mxstep_per_interval;   /* IWORK(6) */
+  int steps_reset_solver;    /* chemsol_params%steps_reset_solver */
+  int nrec_max;              /* leading capacity of touts/record per cell */
+  int tol_policy_j;          /* used when rtol/atol are NULL: chem_set_solver_flags_alt(j) */
+  double RTOL, ATOL;         /* chemsol_params%RTOL/ATOL for the policy */
+} racg_solve_params;
+
+/* The batch replacement for the loop body around `call chem_evol_solve`
+ * (src/disk.f90:1686; semantics of src/chemistry.f90:391-588 with evolT=.false.
+ * and the cpu_time budgets replaced by the MXSTEP budget).
+ *   in : cellpar(ncell,NPAR), y0(ncell,NEQ) [y0(:,NEQ) = Tgas], t0/tmax/dt_first(ncell),
+ *        rtol/atol(ncell,NEQ) or NULL (policy j)
+ *   out: y_final(ncell,NEQ), t_final(ncell), nrec_real(ncell), istate(ncell)
+ *        [DLSODES codes: 2 ok, -1..-7], quality(ncell) [bits 1,2,256,512 as
+ *        src/chemistry.f90:506,528,577-582], stats(ncell,RACG_NSTAT) =
+ *        NST,NFE,NJE,NLU,NQU,n_solve,NERR,n_restart,n_cfail,n_efail,nrec_real,istate,HU,..
+ *        touts(ncell,nrec_max), record(ncell,NEQ,nrec_max): optional (NULL to skip). */
+int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const double* y0,
+                     const double* rtol, const double* atol, const double* t0,
+                     const double* tmax, const double* dt_first, const racg_solve_params* sp,
+                     double* y_final, double* t_final, double* touts, double* record,
+                     int* nrec_real, int* istate, int* quality, double* stats);
+
+/* ---- device-pointer variants (same layouts, buffers already in HBM; `stream` is a
+ * cudaStream_t or NULL) for callers that keep the grid resident on the GPU ---- */
+int racg_rates_dev(racg_handle* h, int ncell, const double* cellpar, double* rates, void* stream);
+int racg_rhs_jac_dev(racg_handle* h, int ncell, const double* cellpar, const double* y,
+                     const double* rates, double* ydot, double* pd, void* stream);
+int racg_solve_batch_dev(racg_handle* h, int ncell, const double* cellpar, const double* y0,
+                         const double* rtol, const double* atol, const double* t0,
+                         const double* tmax, const double* dt_first,
+                         const racg_solve_params* sp, double* y_final, double* t_final,
+                         double* touts, double* record, int* nrec_real, int* istate,
+                         int* quality, double* stats, void* stream);
+/* number of kernel launches issued through this handle so far */
+long racg_launch_count(const racg_handle* h);
+/* per-phase SM-cycle counters of the last racg_solve_batch* call, summed over CTAs:
+ * out[0..15]; returns 0 */
+int racg_phase_cycles(racg_handle* h, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

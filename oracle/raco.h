@@ -98,6 +98,11 @@ void raco_ode_jac_col(const raco_net*, const raco_cfg*, const double* par,
  * raco_net_pattern (pd[NNZ]) */
 void raco_ode_jac_csc(const raco_net*, const raco_cfg*, const double* par,
                       const double* rates, const double* y, double* pd);
+/* rounding scales for parity tests: the same sums with |term| */
+void raco_ode_f_abs(const raco_net*, const raco_cfg*, const double* par, const double* rates,
+                    const double* y, double* out);
+void raco_ode_jac_csc_abs(const raco_net*, const raco_cfg*, const double* par, const double* rates,
+                          const double* y, double* pd);
 /* chem_set_solver_flags_alt(j), src/chemistry.f90:205-268 */
 void raco_set_solver_flags_alt(const raco_net*, int j, double RTOL, double ATOL,
                                double ratioDust2HnucNum, double* rtols, double* atols);

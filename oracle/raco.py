@@ -151,6 +151,20 @@ class Network:
                                _p(np.ascontiguousarray(y)), _p(pd))
         return pd
 
+    def ode_f_abs(self, par, rates, y, cfg=None):
+        cfg = cfg or default_cfg()
+        out = np.zeros(self.NEQ)
+        lib().raco_ode_f_abs(self.h, C.byref(cfg), _p(np.ascontiguousarray(par)), _p(rates),
+                             _p(np.ascontiguousarray(y)), _p(out))
+        return out
+
+    def ode_jac_csc_abs(self, par, rates, y, cfg=None):
+        cfg = cfg or default_cfg()
+        pd = np.zeros(self.NNZ)
+        lib().raco_ode_jac_csc_abs(self.h, C.byref(cfg), _p(np.ascontiguousarray(par)), _p(rates),
+                                   _p(np.ascontiguousarray(y)), _p(pd))
+        return pd
+
     def solver_flags_alt(self, j, RTOL, ATOL, D):
         rt = np.zeros(self.NEQ)
         at = np.zeros(self.NEQ)

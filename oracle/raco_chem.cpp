@@ -394,6 +394,39 @@ void raco_ode_jac_csc(const raco_net* h, const raco_cfg* c, const double* par, c
   ode_jac_csc(h->net, *c, par, rates, y, pd);
 }
 
+// Rounding scales for the parity tests: the same sums with every term taken in
+// absolute value (sum_r |flux_r| per participating species / per Jacobian slot).
+void raco_ode_f_abs(const raco_net* h, const raco_cfg* c, const double* par, const double* rates,
+                    const double* y, double* out) {
+  const Net& n = h->net;
+  for (int i = 0; i < n.NEQ; ++i) out[i] = 0.0;
+  for (int i = 0; i < n.R; ++i) {
+    double r;
+    if (!flux(n, *c, par, rates, y, i, r)) continue;
+    r = std::fabs(r);
+    for (int j = 0; j < n.n_reac[i]; ++j) out[n.reac[3 * i + j] - 1] += r;
+    for (int j = 0; j < n.n_prod[i]; ++j) out[n.prod[4 * i + j] - 1] += r;
+  }
+}
+void raco_ode_jac_csc_abs(const raco_net* h, const raco_cfg* c, const double* par, const double* rates,
+                          const double* y, double* pd) {
+  const Net& n = h->net;
+  const int NEQ = n.NEQ;
+  for (int k = 0; k < n.NNZ; ++k) pd[k] = 0.0;
+  for (int i = 0; i < n.R; ++i) {
+    int cols[2] = {n.reac[3 * i], n.n_reac[i] >= 2 ? n.reac[3 * i + 1] : 0};
+    int ncol = (cols[1] > 0 && cols[1] != cols[0]) ? 2 : 1;
+    for (int q = 0; q < ncol; ++q) {
+      int j = cols[q];
+      double r;
+      if (!dflux(n, *c, par, rates, y, i, j, r)) break;
+      r = std::fabs(r);
+      for (int k = 0; k < n.n_reac[i]; ++k) pd[n.slot_of[(size_t)(n.reac[3 * i + k] - 1) + (size_t)(j - 1) * NEQ]] += r;
+      for (int k = 0; k < n.n_prod[i]; ++k) pd[n.slot_of[(size_t)(n.prod[4 * i + k] - 1) + (size_t)(j - 1) * NEQ]] += r;
+    }
+  }
+}
+
 // chem_set_solver_flags_alt(j), src/chemistry.f90:205-268
 void raco_set_solver_flags_alt(const raco_net* h, int j, double RTOL, double ATOL, double D,
                                double* rt, double* at) {

@@ -1,0 +1,245 @@
+"""GPU parity tests: libracg.so (CUDA, through the C-ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): reaction indexing and sparsity pattern bit-exact;
+rate coefficients / RHS / Jacobian to rounding (they differ from the oracle only by
+libm vs CUDA pow/exp and by summation order); abundances after integration within
+1e-3 relative for species above 1e-12 of n_H at every output time.
+"""
+import numpy as np
+import pytest
+
+from conftest import IC_GARROD, NET_A, NET_B
+
+pytestmark = pytest.mark.gpu
+
+RTOL_X = 1e-3      # north_star tolerance on abundances
+X_FLOOR = 1e-12    # ... for species above this abundance
+
+
+@pytest.fixture(scope="module")
+def setupA(rb, oracle):
+    net = rb.ChemNetwork(NET_A)
+    sol = net.create_solver()
+    onet = oracle.Network(NET_A)
+    y0s = net.chem_load_initial_abundances(IC_GARROD)
+    return rb, net, sol, onet, y0s
+
+
+def _cells(rb, net, y0s, ncell, stratified=False):
+    par = rb.synth.stratified_params(ncell) if stratified else rb.synth.cell_params(ncell)
+    y0 = rb.synth.initial_state(y0s, par, net.index("Grain0"))
+    return par, y0
+
+
+def test_pattern_bit_exact_on_gpu_handle(setupA):
+    rb, net, sol, onet, _ = setupA
+    ia, ja = sol.pattern()
+    assert np.array_equal(ia, onet.ia) and np.array_equal(ja, onet.ja)
+    assert sol.NNZ == 13469 and sol.NNZ_diag == 13472
+
+
+def test_rates_match_oracle(setupA):
+    rb, net, sol, onet, y0s = setupA
+    par, _ = _cells(rb, net, y0s, 96)
+    k = sol.chem_cal_rates(par)
+    assert k.shape == (96, net.R)
+    worst = 0.0
+    for c in range(96):
+        ko = onet.cal_rates(par[c])
+        assert np.array_equal(k[c] == 0.0, ko == 0.0), "zero pattern (duplicate sets, T ranges) differs"
+        nz = ko != 0.0
+        worst = max(worst, np.max(np.abs(k[c][nz] - ko[nz]) / np.abs(ko[nz])))
+    assert worst < 1e-12, worst
+
+
+def test_rates_edge_cases(setupA):
+    """Tgas at duplicate-set T-range edges, zero UV / zero Av, sig_dust -> 0."""
+    rb, net, sol, onet, y0s = setupA
+    par, _ = _cells(rb, net, y0s, 8)
+    P = rb.synth.P
+    par[0, P["Tgas"]] = 300.0
+    par[1, P["Tgas"]] = 10.0
+    par[2, P["Tgas"]] = 41000.0
+    par[3, P["G0_UV_toStar"]] = 0.0; par[3, P["G0_UV_H2phd"]] = 0.0; par[3, P["G0_UV_toStar_photoDesorb"]] = 0.0
+    par[4, P["sigdust_ave"]] = 0.0
+    par[5, P["Av_toISM"]] = 0.0; par[5, P["Av_toStar"]] = 0.0; par[5, P["Ncol_toISM"]] = 0.0
+    par[6, P["Tdust"]] = 5.0
+    par[7, P["phflux_Lya"]] = 1e12
+    k = sol.chem_cal_rates(par)
+    for c in range(8):
+        ko = onet.cal_rates(par[c])
+        assert np.array_equal(k[c] == 0.0, ko == 0.0)
+        nz = ko != 0.0
+        assert np.max(np.abs(k[c][nz] - ko[nz]) / np.abs(ko[nz])) < 1e-12
+
+
+def _rel_to_scale(a, b, scale):
+    return np.max(np.abs(a - b) / scale)
+
+
+def test_rhs_jac_match_oracle(setupA):
+    rb, net, sol, onet, y0s = setupA
+    ncell = 70   # ragged: not a multiple of the tile sizes (4 and 32)
+    par, y0 = _cells(rb, net, y0s, ncell)
+    rng = np.random.default_rng(1)
+    y = y0.copy()
+    # a populated state: random abundances over 20 decades, a few negative (sign-flip branches)
+    y[:, :net.N] = 10.0 ** rng.uniform(-25, -4, size=(ncell, net.N))
+    y[:, :net.N] *= np.where(rng.random((ncell, net.N)) < 0.02, -1.0, 1.0)
+    y[:8] = y0[:8]   # and the hard start: all ions exactly zero
+    k = np.zeros((ncell, net.R))
+    for c in range(ncell):
+        k[c] = onet.cal_rates(par[c])
+    ydot, pd = sol.chem_ode_f_jac(par, y, k)
+    assert ydot.shape == (ncell, net.NEQ) and pd.shape == (ncell, sol.NNZ)
+    for c in range(ncell):
+        fo = onet.ode_f(par[c], k[c], y[c])
+        # cancellation makes a relative test against |ydot| meaningless: the rounding scale
+        # of a sum is the sum of |terms|, which the oracle provides
+        fa = onet.ode_f_abs(par[c], k[c], y[c])
+        assert _rel_to_scale(ydot[c], fo, np.maximum(fa, 1e-300)) < 1e-13
+        jo = onet.ode_jac_csc(par[c], k[c], y[c])
+        ja_ = onet.ode_jac_csc_abs(par[c], k[c], y[c])
+        assert np.array_equal(pd[c][ja_ == 0.0], jo[ja_ == 0.0])
+        assert _rel_to_scale(pd[c], jo, np.maximum(ja_, 1e-300)) < 1e-13
+        assert ydot[c, net.N] == 0.0
+
+
+def _compare_trajectories(res, oracle_runs, net, nrec):
+    """max relative difference over species above X_FLOOR at every output time."""
+    worst = 0.0
+    where = None
+    for c, orun in enumerate(oracle_runs):
+        n_o = orun["n_record_real"]
+        assert res["n_record_real"][c] == n_o
+        np.testing.assert_allclose(res["touts"][c, :n_o], orun["touts"][:n_o], rtol=1e-12)
+        for i in range(n_o):
+            a = res["record"][c, :net.N, i]
+            b = orun["record"][i, :net.N]
+            m = np.abs(b) > X_FLOOR
+            if m.any():
+                rel = np.abs(a[m] - b[m]) / np.abs(b[m])
+                if rel.max() > worst:
+                    worst = rel.max()
+                    where = (c, i, np.array(net.names)[m][np.argmax(rel)])
+    return worst, where
+
+
+def test_evol_solve_matches_oracle_every_output_time(setupA):
+    """8 cells, rate06-withgrain, 1e-8 -> 1e6 yr, reference tolerances: every output time."""
+    rb, net, sol, onet, y0s = setupA
+    ncell = 8
+    par, y0 = _cells(rb, net, y0s, ncell)
+    res = sol.chem_evol_solve(par, y0, want_record=True)
+    assert np.all(res["istate"] == 2) and np.all(res["quality"] == 0)
+    runs = []
+    for c in range(ncell):
+        rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[c, 6])
+        runs.append(onet.evol_solve(par[c], y0[c], rt, at))
+        assert runs[-1]["quality"] == 0
+    worst, where = _compare_trajectories(res, runs, net, res["nrec_max"])
+    assert worst < RTOL_X, (worst, where)
+    # final state and t_final
+    for c in range(ncell):
+        assert res["t_final"][c] == runs[c]["t_final"] == 1e6
+        assert res["y"][c, net.N] == par[c, 0]
+    # step counts are of the same order as the oracle's (same controller)
+    nst_g = res["stats"][:, 0]
+    nst_o = np.array([r["stats"][0] for r in runs])
+    assert np.all(np.abs(nst_g - nst_o) < 0.25 * nst_o + 50), (nst_g, nst_o)
+
+
+def test_evol_solve_stratified_and_policy_tolerances(setupA):
+    """config-5 strata, explicit rtol/atol arrays equal to the in-kernel policy."""
+    rb, net, sol, onet, y0s = setupA
+    ncell = 8
+    par, y0 = _cells(rb, net, y0s, ncell, stratified=True)
+    rt, at = sol.chem_set_solver_flags_alt(1, 1e-4, 1e-30, par)
+    for c in range(ncell):
+        ro, ao = onet.solver_flags_alt(1, 1e-4, 1e-30, par[c, 6])
+        assert np.array_equal(rt[c], ro) and np.array_equal(at[c], ao)
+    r1 = sol.chem_evol_solve(par, y0, rtol=rt, atol=at)
+    r2 = sol.chem_evol_solve(par, y0)
+    assert np.array_equal(r1["y"], r2["y"]), "explicit tolerances and policy j=1 must be identical"
+    for c in range(ncell):
+        o = onet.evol_solve(par[c], y0[c], rt[c], at[c], want_record=False)
+        m = np.abs(o["y"][:net.N]) > X_FLOOR
+        rel = np.abs(r1["y"][c, :net.N][m] - o["y"][:net.N][m]) / np.abs(o["y"][:net.N][m])
+        assert rel.max() < RTOL_X, (c, rel.max())
+
+
+def test_evol_solve_invariants_and_determinism(setupA):
+    """size-independent properties on a larger batch: element conservation (the check the
+    reference prints, src/disk.f90:1691-1702), charge neutrality, run-to-run bit-identity,
+    independence of batch composition (work-queue order)."""
+    rb, net, sol, onet, y0s = setupA
+    ncell = 300
+    par, y0 = _cells(rb, net, y0s, ncell)
+    r1 = sol.chem_evol_solve(par, y0, want_touts=False)
+    assert np.all(r1["istate"] == 2), np.unique(r1["istate"], return_counts=True)
+    el = net.elements.astype(float)            # [N,20]
+    e0 = y0[:, :net.N] @ el
+    e1 = r1["y"][:, :net.N] @ el
+    for k in range(3, 20):                      # nuclei (skip charge, electrons, grains)
+        tot = np.abs(e0[:, k]).max()
+        if tot > 0:
+            assert np.max(np.abs(e1[:, k] - e0[:, k]) / np.maximum(np.abs(e0[:, k]), 1e-300)) < 1e-6, k
+    charge = r1["y"][:, :net.N] @ el[:, 0]
+    assert np.max(np.abs(charge)) < 1e-6 * np.max(np.abs(r1["y"][:, net.index("E-") - 1])) + 1e-12
+    r2 = sol.chem_evol_solve(par, y0, want_touts=False)
+    assert np.array_equal(r1["y"], r2["y"]) and np.array_equal(r1["stats"], r2["stats"])
+    sub = np.arange(0, ncell, 7)
+    r3 = sol.chem_evol_solve(par[sub], y0[sub], want_touts=False)
+    assert np.array_equal(r3["y"], r1["y"][sub])
+
+
+def test_evol_solve_edge_cases(setupA):
+    """empty batch, single cell, per-cell t_max (n_record varies per cell), tiny MXSTEP."""
+    rb, net, sol, onet, y0s = setupA
+    par, y0 = _cells(rb, net, y0s, 3)
+    r0 = sol.chem_evol_solve(par[:0], y0[:0])
+    assert r0["y"].shape == (0, net.NEQ)
+    tmax = np.array([1e2, 1e4, 1e6])
+    res = sol.chem_evol_solve(par, y0, t_max=tmax)
+    for c in range(3):
+        rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[c, 6])
+        o = onet.evol_solve(par[c], y0[c], rt, at, t_max=float(tmax[c]), want_record=False)
+        assert res["n_record_real"][c] == o["n_record_real"]
+        assert res["t_final"][c] == o["t_final"] == tmax[c]
+        m = np.abs(o["y"][:net.N]) > X_FLOOR
+        rel = np.abs(res["y"][c, :net.N][m] - o["y"][:net.N][m]) / np.abs(o["y"][:net.N][m])
+        assert rel.max() < RTOL_X
+    # MXSTEP exhausted: ISTATE=-1 path, error counting and quality bits as the reference
+    res = sol.chem_evol_solve(par[:1], y0[:1], mxstep_per_interval=3)
+    rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[0, 6])
+    o = onet.evol_solve(par[0], y0[0], rt, at, mxstep=3, want_record=False)
+    assert res["quality"][0] == o["quality"]
+    assert res["n_record_real"][0] == o["n_record_real"]
+    assert res["stats"][0, 6] == o["stats"][6]          # NERR
+    assert abs(res["t_final"][0] - o["t_final"]) <= 1e-6 * abs(o["t_final"])
+
+
+def test_rate12_network(rb, oracle):
+    """config 3 network (UMIST rate12 with grains): rates, RHS/Jacobian and 4 cells."""
+    net = rb.ChemNetwork(NET_B)
+    sol = net.create_solver()
+    onet = oracle.Network(NET_B)
+    ia, ja = sol.pattern()
+    assert np.array_equal(ia, onet.ia) and np.array_equal(ja, onet.ja) and sol.NNZ == 18205
+    y0s = net.chem_load_initial_abundances(IC_GARROD)
+    par = rb.synth.cell_params(4)
+    y0 = rb.synth.initial_state(y0s, par, net.index("Grain0"))
+    k = sol.chem_cal_rates(par)
+    for c in range(4):
+        ko = onet.cal_rates(par[c])
+        nz = ko != 0
+        assert np.array_equal(k[c] == 0, ko == 0)
+        assert np.max(np.abs(k[c][nz] - ko[nz]) / np.abs(ko[nz])) < 1e-12
+    res = sol.chem_evol_solve(par, y0)
+    assert np.all(res["istate"] == 2)
+    for c in range(4):
+        rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[c, 6])
+        o = onet.evol_solve(par[c], y0[c], rt, at, want_record=False)
+        m = np.abs(o["y"][:net.N]) > X_FLOOR
+        rel = np.abs(res["y"][c, :net.N][m] - o["y"][:net.N][m]) / np.abs(o["y"][:net.N][m])
+        assert rel.max() < RTOL_X, (c, rel.max())
