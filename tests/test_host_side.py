@@ -1,0 +1,160 @@
+"""CPU tests of the product's host side: the C++ loader mirror and the symbolic setup
+against the (independently written) oracle, the C-ABI surface, the synthetic generator
+and the multi-GPU sharding logic (gloo, world_size 2).  No compute call needs a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import IC_GARROD, IC_LOMETAL, NET_A, NET_B, NET_C, ROOT
+
+
+@pytest.mark.parametrize("path", [NET_A, NET_B, NET_C])
+def test_loader_and_pattern_bit_exact_vs_oracle(rb, oracle, path):
+    """Reaction indexing and the sparsity pattern must be bit-exact (north_star)."""
+    net = rb.ChemNetwork(path)
+    o = oracle.Network(path)
+    assert (net.R, net.N) == (o.R, o.N)
+    assert net.names == o.names and net.ctype == o.ctype
+    for a, b in ((net.reac, o.reac), (net.prod, o.prod), (net.n_reac, o.n_reac), (net.n_prod, o.n_prod),
+                 (net.itype, o.itype), (net.ABC, o.ABC), (net.T_range, o.T_range), (net.elements, o.elements),
+                 (net.mass_num, o.mass_num), (net.dupli_ptr, o.dupli_ptr),
+                 (net.dupli_list[:o.n_dupli], o.dupli_list[:o.n_dupli])):
+        assert np.array_equal(a, b)
+    assert np.array_equal(net.vib_freq, o.vib_freq, equal_nan=True)
+    assert np.array_equal(net.Edesorb, o.Edesorb, equal_nan=True)
+    sol = net.create_solver()          # host-only handle when no GPU is visible
+    ia, ja = sol.pattern()
+    assert np.array_equal(ia, o.ia) and np.array_equal(ja, o.ja)
+    assert (sol.NNZ, sol.NNZ_diag) == (o.NNZ, o.nnz_diag)
+    perm = sol.ordering()
+    assert sorted(perm.tolist()) == list(range(1, net.N + 1))
+    # fill of the product's ordering is within 10 % of the oracle's minimum-degree ordering
+    # (oracle counts the T slot's full row and column as well)
+    assert sol.nnz_lu <= 1.10 * o.nnz_ldu
+    for ic in (IC_GARROD, IC_LOMETAL):
+        assert np.array_equal(net.chem_load_initial_abundances(ic), o.load_initial_abundances(ic))
+
+
+def test_solver_flags_alt_matches_oracle(rb, oracle):
+    net = rb.ChemNetwork(NET_A)
+    o = oracle.Network(NET_A)
+    sol = net.create_solver()
+    par = rb.synth.cell_params(5)
+    for j in (1, 2, 3, 4, 6):
+        rt, at = sol.chem_set_solver_flags_alt(j, 1e-4, 1e-30, par)
+        for c in range(5):
+            ro, ao = o.solver_flags_alt(j, 1e-4, 1e-30, par[c, 6])
+            assert np.array_equal(rt[c], ro) and np.array_equal(at[c], ao)
+    assert sol.n_record(0.0, 1e6, 1e-8, 1.1) == 316
+
+
+def test_c_abi_exports_every_declared_symbol(rb):
+    """libracg.so loads and exports every function include/racg.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "racg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(racg_[a-z_]+)\s*\(", hdr))
+    assert len(names) >= 15
+    L = C.CDLL(rb.lib_path())
+    for n in sorted(names):
+        assert hasattr(L, n), n
+    out = subprocess.run(["nm", "-D", "--defined-only", rb.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (racg_\w+)", out))
+    assert names <= exported
+
+
+def test_no_gpu_means_loud_failure_not_fallback(rb):
+    """Without a CUDA device every compute entry point fails with RACG_ERR_CUDA."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    net = rb.ChemNetwork(NET_A)
+    sol = net.create_solver()
+    par = rb.synth.cell_params(2)
+    with pytest.raises(rb.RacgError, match="no CPU fallback"):
+        sol.chem_cal_rates(par)
+    y0 = rb.synth.initial_state(net.chem_load_initial_abundances(IC_GARROD), par, net.index("Grain0"))
+    with pytest.raises(rb.RacgError, match="no CPU fallback"):
+        sol.chem_evol_solve(par, y0)
+
+
+def test_product_never_touches_the_oracle():
+    """The product path must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "rac-2d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", "Makefile")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "raco" not in src and "libraco" not in src, os.path.join(dirpath, f)
+    out = subprocess.run(["ldd", os.path.join(pkg, "libracg.so")], capture_output=True, text=True).stdout
+    assert "raco" not in out
+
+
+def test_bad_network_inputs_are_rejected(rb):
+    net = rb.ChemNetwork(NET_A)
+    bad = net.itype.copy()
+    # a type-21 (ion + grain) reaction whose reactants are both grains -> the reference's error_stop
+    i21 = int(np.nonzero(net.itype == 21)[0][0])
+    saved = net.reac[i21].copy()
+    g0 = net.index("Grain0")
+    net.reac[i21, 0] = g0
+    net.reac[i21, 1] = net.index("Grain-")
+    with pytest.raises(rb.RacgError, match="type 21"):
+        net.create_solver()
+    net.reac[i21] = saved
+    cfg = rb.default_cfg()
+    cfg.H2_form_use_moeq = 1
+    with pytest.raises(rb.RacgError, match="not supported"):
+        net.create_solver(cfg)
+    del bad
+
+
+def test_synthetic_cells_deterministic_and_prefix_stable(rb):
+    a = rb.synth.cell_params(100)
+    b = rb.synth.cell_params(40, first_cell=30)
+    assert np.array_equal(a[30:70], b)
+    assert np.array_equal(a, rb.synth.cell_params(100))
+    P = rb.synth.P
+    assert a[:, P["n_gas"]].min() >= 1e3 and a[:, P["n_gas"]].max() <= 1e13
+    assert a[:, P["Tgas"]].min() >= 8 and a[:, P["Tdust"]].min() >= 5
+    assert np.all(a[:, P["ndust_tot"]] == a[:, P["n_gas"]] * a[:, P["ratioDust2HnucNum"]])
+    s = rb.synth.stratified_params(16)
+    assert np.all(s[0::4, P["n_gas"]] >= 1e9) and np.all(s[2::4, P["Av_toStar"]] < 1.0)
+
+
+def test_world_size_2_sharding_with_gloo(tmp_path):
+    """N>1 path on CPU: each rank owns a contiguous block of the cell stream, results are
+    gathered with one all_gather; the union equals the single-rank batch."""
+    script = tmp_path / "shard.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np, torch, torch.distributed as dist
+import rac2d_b200 as rb
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ncell = 24
+par = rb.synth.cell_params(ncell, first_cell=rank * ncell)
+# stand-in for the solve: a deterministic per-cell function of the inputs
+yf = torch.from_numpy(np.ascontiguousarray(par[:, :8].T.copy()))
+out = torch.empty((world,) + tuple(yf.shape), dtype=yf.dtype)
+dist.all_gather_into_tensor(out.view(-1), yf.view(-1))
+full = rb.synth.cell_params(world * ncell)
+for r in range(world):
+    assert np.array_equal(out[r].numpy().T, full[r * ncell:(r + 1) * ncell, :8])
+t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert t.item() == world
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+''')
+    env = dict(os.environ)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
