@@ -283,5 +283,5 @@ class ChemSolver:
         out = np.zeros(16)
         _check(lib().racg_phase_cycles(self.h, _p(out)))
         names = ["rates", "f", "jac", "fact_head", "fact_schur", "fact_tail", "solve", "vec", "io",
-                 "total", "ncell"]
+                 "total", "ncell", "pbuild", "tail_inv"]
         return {n: out[i] for i, n in enumerate(names)}

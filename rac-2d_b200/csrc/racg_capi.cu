@@ -11,7 +11,7 @@
 
 namespace racg {
 // racg_integrate.cu
-size_t integrate_smem_bytes(const DevNet& net, int npart_rhs, int npart_jac);
+size_t integrate_smem_bytes(const DevNet& net);
 size_t integrate_ws_doubles(const DevNet& net);
 cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nblocks, size_t smem, cudaStream_t stream);
 // racg_batch.cu
@@ -62,6 +62,23 @@ static int upload_gather(racg_handle* h, const Gather& g, GatherDev& d) {
   if ((rc = upload(h, g.ent, &d.ent))) return rc;
   if ((rc = upload(h, g.comb_row, &d.comb_row))) return rc;
   if ((rc = upload(h, g.comb_ptr, &d.comb_ptr))) return rc;
+  d.sub_add = nullptr; d.comb_add = nullptr;
+  if (!g.sub_add.empty()) {
+    if ((rc = upload(h, g.sub_add, &d.sub_add))) return rc;
+    if ((rc = upload(h, g.comb_add, &d.comb_add))) return rc;
+  }
+  return 0;
+}
+
+static int upload_ell(racg_handle* h, const HostNet::Ell& e, EllDev& d) {
+  d.nblk = e.nblk; d.npartial = e.npartial; d.ncombine = e.ncombine; d.nval = e.nval;
+  int rc;
+  if ((rc = upload(h, e.blk_off, &d.blk_off))) return rc;
+  if ((rc = upload(h, e.blk_width, &d.blk_width))) return rc;
+  if ((rc = upload(h, e.sub_target, &d.sub_target))) return rc;
+  if ((rc = upload(h, e.col, &d.col))) return rc;
+  if ((rc = upload(h, e.comb_row, &d.comb_row))) return rc;
+  if ((rc = upload(h, e.comb_ptr, &d.comb_ptr))) return rc;
   return 0;
 }
 
@@ -149,7 +166,9 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
   DevNet& dn = h->dn;
   memset(&dn, 0, sizeof(dn));
   dn.R = hn.R; dn.N = hn.N; dn.NEQ = hn.NEQ; dn.n = hn.n; dn.nh = hn.nh; dn.nt = hn.nt;
-  dn.nslots = hn.nslots; dn.nJ = hn.nslots + hn.nt * hn.nt; dn.nsat = hn.nsat; dn.NNZ = hn.NNZ;
+  dn.nsat = hn.nsat; dn.NNZ = hn.NNZ;
+  dn.n_hh = hn.n_hh; dn.n_ub = hn.n_ub; dn.n_lc = hn.n_lc; dn.o_ub = hn.o_ub; dn.o_lc = hn.o_lc;
+  dn.o_tl = hn.o_tl; dn.ldt = hn.ldt; dn.nstore = hn.nstore;
   dn.cfg = hn.cfg;
   bdf_coefficients(dn);
   int rc;
@@ -169,10 +188,23 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
   }
   UP(hn.fw, fw); UP(hn.sat_c, sat_c);
   if ((rc = upload_gather(h, hn.rhs, dn.rhs))) return rc;
-  if ((rc = upload_gather(h, hn.jac, dn.jac))) return rc;
-  UP(hn.row_ptr, row_ptr); UP(hn.row_nl, row_nl); UP(hn.col, col); UP(hn.perm, perm);
-  dn.nflev = (int)hn.flev_ptr.size() - 1; UP(hn.flev_ptr, flev_ptr); UP(hn.flev_rows, flev_rows);
-  dn.nsu = (int)hn.su_ptr.size() - 1; UP(hn.su_ptr, su_ptr); UP(hn.su_rows, su_rows);
+  if ((rc = upload_gather(h, hn.jac[0], dn.jac[0]))) return rc;
+  if ((rc = upload_gather(h, hn.jac[1], dn.jac[1]))) return rc;
+  UP(hn.hh_ptr, hh_ptr); UP(hn.hh_nl, hh_nl); UP(hn.hh_col, hh_col);
+  UP(hn.ub_col, ub_col); UP(hn.ub_ellpos, ub_ellpos);
+  UP(hn.lc_ptr, lc_ptr); UP(hn.lc_col, lc_col); UP(hn.lc_ellpos, lc_ellpos);
+  if ((rc = upload_ell(h, hn.ubE, dn.ubE))) return rc;
+  if ((rc = upload_ell(h, hn.lcE, dn.lcE))) return rc;
+  UP(hn.perm, perm); UP(hn.tail_order, tail_order);
+  {
+    const int* p;
+    if ((rc = upload(h, hn.pivmeta, &p))) return rc; dn.pivmeta = (const int4*)p;
+    if ((rc = upload(h, hn.fmeta, &p))) return rc; dn.fmeta = (const int4*)p;
+    if ((rc = upload(h, hn.bmeta, &p))) return rc; dn.bmeta = (const int4*)p;
+  }
+  dn.flev_nfat_rows = hn.flev_ptr[hn.nfat_f]; dn.su_nfat_rows = hn.su_ptr[hn.nfat_b];
+  dn.nflev = (int)hn.flev_ptr.size() - 1; dn.nfat_f = hn.nfat_f; UP(hn.flev_ptr, flev_ptr); UP(hn.flev_rows, flev_rows);
+  dn.nsu = (int)hn.su_ptr.size() - 1; dn.nfat_b = hn.nfat_b; UP(hn.su_ptr, su_ptr); UP(hn.su_rows, su_rows);
   dn.iH = hn.iH; dn.iE = hn.iE; dn.igH = hn.igH; dn.igH2 = hn.igH2; dn.igH2O = hn.igH2O;
   dn.iGrain0 = hn.iGrain0; dn.iGrainM = hn.iGrainM; dn.iGrainP = hn.iGrainP;
   UP(hn.hc_idx, hc_idx);
@@ -193,7 +225,7 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
   }
 #undef UP
   // integrator: one persistent CTA per SM, L2-resident workspace per CTA
-  h->smem_int = integrate_smem_bytes(dn, hn.rhs.npartial, hn.jac.npartial);
+  h->smem_int = integrate_smem_bytes(dn);
   if (h->smem_int > (size_t)prop.sharedMemPerBlockOptin)
     return fail(RACG_ERR_UNSUPPORTED, "network too large for the shared-memory layout of the integrator: " +
                                       std::to_string(h->smem_int) + " B needed");

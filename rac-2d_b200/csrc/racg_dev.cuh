@@ -1,6 +1,7 @@
 // racg_dev.cuh -- device-side table descriptors shared by the kernels of libracg.
 #pragma once
 #include <cstdint>
+#include <vector_types.h>
 #include "../../include/racg.h"
 
 namespace racg {
@@ -13,10 +14,21 @@ struct GatherDev {
   const uint32_t* ent;
   const int* comb_row;       // [ncombine]
   const int* comb_ptr;       // [ncombine+1]
+  const uint8_t* sub_add;    // optional (null = always store)
+  const uint8_t* comb_add;
+};
+
+// ELL copy of a coupling block for the solve's SpMV passes (values live in the
+// per-CTA workspace at the same positions as col)
+struct EllDev {
+  int nblk, npartial, ncombine, nval;
+  const int* blk_off; const int* blk_width; const int* sub_target;
+  const uint16_t* col;
+  const int* comb_row; const int* comb_ptr;
 };
 
 struct DevNet {
-  int R, N, NEQ, n, nh, nt, nslots, nJ, nsat, NNZ;
+  int R, N, NEQ, n, nh, nt, nsat, NNZ;
   // rates
   const int* rcode;
   const double *rA, *rB, *rC, *rTlo, *rThi, *rX;
@@ -27,14 +39,21 @@ struct DevNet {
   // flux
   const uint32_t* fw;
   const double* sat_c;
-  GatherDev rhs, jac;
-  // LU
-  const int* row_ptr;
-  const int* row_nl;
-  const uint16_t* col;
+  GatherDev rhs, jac[2];
+  // LU storage layout (see racg_host.hpp)
+  int n_hh, n_ub, n_lc, o_ub, o_lc, o_tl, ldt, nstore;
+  const int* hh_ptr; const int* hh_nl; const uint16_t* hh_col;
+  const uint16_t* ub_col; const int* ub_ellpos;   // [n_ub] tail-local column / position in the ELL copy
+  const int* lc_ptr; const uint16_t* lc_col; const int* lc_ellpos;
+  EllDev ubE, lcE;
   const int* perm;           // permuted -> original species
-  int nflev; const int* flev_ptr; const int* flev_rows;
-  int nsu;   const int* su_ptr;   const int* su_rows;
+  int nflev, nfat_f; const int* flev_ptr; const int* flev_rows;
+  int nsu, nfat_b;   const int* su_ptr;   const int* su_rows;
+  int flev_nfat_rows, su_nfat_rows;   // rows in the fat levels (= flev_ptr[nfat_f], su_ptr[nfat_b])
+  const int* tail_order;     // [nt]
+  const int4* pivmeta;       // [nh]
+  const int4* fmeta;         // [nh] forward-level order
+  const int4* bmeta;         // [nh] backward-level order
   // species of the sanity test (src/chemistry.f90:520-526), 0-based or -1
   int iH, iE, igH, igH2, igH2O, iGrain0, iGrainM, iGrainP;
   const int* hc_idx;         // [10]

@@ -226,7 +226,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   hn.nsat = (int)hn.sat_c.size();
   build_gather(hn.rhs, sp_rows, 32);
 
-  // ---- species-block pattern and fill-reducing ordering (minimum degree on M + M^T)
+  // ---- species-block pattern and fill-reducing ordering
   const int n = N;
   const int W = (n + 63) / 64;
   std::vector<uint64_t> A((size_t)n * W, 0);   // A[row][col] bits, unsymmetric pattern incl. diagonal
@@ -235,82 +235,164 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   for (int c = 0; c < n; ++c)
     for (int k = hn.ia[c] - 1; k < hn.ia[c + 1] - 1; ++k) { int r = hn.ja[k] - 1; if (r < n) setb(A, r, c); }
   for (int i = 0; i < n; ++i) setb(A, i, i);
-  std::vector<uint64_t> G((size_t)n * W, 0);   // symmetric elimination graph (no self loops)
+  std::vector<uint64_t> G0((size_t)n * W, 0);   // symmetric graph of M + M^T (no self loops)
   for (int r = 0; r < n; ++r)
-    for (int c = 0; c < n; ++c) if (r != c && (getb(A, r, c) || getb(A, c, r))) { setb(G, r, c); setb(G, c, r); }
-  hn.perm.assign(n, 0); hn.iperm.assign(n, 0);
-  {
+    for (int c = 0; c < n; ++c) if (r != c && (getb(A, r, c) || getb(A, c, r))) { setb(G0, r, c); setb(G0, c, r); }
+  // elimination on the bitset graph; multi = ratio for multiple elimination of an
+  // independent set of near-minimum-degree vertices per round (shallower elimination
+  // tree = fewer solve levels); nstop = number of pivots to take this way
+  auto eliminate = [&](std::vector<uint64_t>& G, std::vector<char>& done, std::vector<int>& order, int v) {
+    done[v] = 1; order.push_back(v);
+    std::vector<uint64_t> nb(G.begin() + (size_t)v * W, G.begin() + (size_t)v * W + W);
+    for (int a = 0; a < n; ++a) {
+      if (!((nb[a >> 6] >> (a & 63)) & 1ull)) continue;
+      uint64_t* ga = &G[(size_t)a * W];
+      for (int w = 0; w < W; ++w) ga[w] |= nb[w];
+      ga[a >> 6] &= ~(1ull << (a & 63));
+      ga[v >> 6] &= ~(1ull << (v & 63));
+    }
+    for (int w = 0; w < W; ++w) G[(size_t)v * W + w] = 0;
+  };
+  auto degree = [&](const std::vector<uint64_t>& G, int v) { int d = 0; for (int w = 0; w < W; ++w) d += __builtin_popcountll(G[(size_t)v * W + w]); return d; };
+  auto min_degree_order = [&](double multi, int nmulti, int* clique_start) {
+    std::vector<uint64_t> G = G0;
     std::vector<char> done(n, 0);
-    std::vector<int> deg(n);
-    auto degree = [&](int v) { int d = 0; for (int w = 0; w < W; ++w) d += __builtin_popcountll(G[(size_t)v * W + w]); return d; };
-    for (int v = 0; v < n; ++v) deg[v] = degree(v);
-    int clique_start = -1;
-    for (int step = 0; step < n; ++step) {
-      int best = -1;
-      for (int v = 0; v < n; ++v) if (!done[v] && (best < 0 || deg[v] < deg[best])) best = v;
-      if (clique_start < 0 && deg[best] >= n - step - 1) clique_start = step;
-      done[best] = 1; hn.perm[step] = best; hn.iperm[best] = step;
-      // neighbours of best become a clique
-      std::vector<uint64_t> nb(G.begin() + (size_t)best * W, G.begin() + (size_t)best * W + W);
-      for (int a = 0; a < n; ++a) {
-        if (!((nb[a >> 6] >> (a & 63)) & 1ull)) continue;
-        uint64_t* ga = &G[(size_t)a * W];
-        for (int w = 0; w < W; ++w) ga[w] |= nb[w];
-        ga[a >> 6] &= ~(1ull << (a & 63));
-        ga[best >> 6] &= ~(1ull << (best & 63));
-        deg[a] = degree(a);
+    std::vector<int> order;
+    if (clique_start) *clique_start = -1;
+    while ((int)order.size() < n) {
+      int dmin = n + 1;
+      for (int v = 0; v < n; ++v) if (!done[v]) dmin = std::min(dmin, degree(G, v));
+      if (clique_start && *clique_start < 0 && dmin >= n - (int)order.size() - 1) *clique_start = (int)order.size();
+      if ((int)order.size() < nmulti && multi > 1.0) {
+        std::vector<std::pair<int, int>> cand;
+        for (int v = 0; v < n; ++v) if (!done[v]) { int d = degree(G, v); if (d <= multi * dmin) cand.push_back({d, v}); }
+        std::sort(cand.begin(), cand.end());
+        std::vector<uint64_t> blocked(W, 0);
+        std::vector<int> chosen;
+        for (auto& dv : cand) {
+          int v = dv.second;
+          if ((blocked[v >> 6] >> (v & 63)) & 1ull) continue;
+          if ((int)order.size() + (int)chosen.size() >= nmulti) break;
+          chosen.push_back(v);
+          for (int w = 0; w < W; ++w) blocked[w] |= G[(size_t)v * W + w];
+          blocked[v >> 6] |= 1ull << (v & 63);
+        }
+        for (int v : chosen) eliminate(G, done, order, v);
+      } else {
+        int best = -1, bd = n + 1;
+        for (int v = 0; v < n; ++v) if (!done[v]) { int d = degree(G, v); if (d < bd) { bd = d; best = v; } }
+        eliminate(G, done, order, best);
       }
-      for (int w = 0; w < W; ++w) G[(size_t)best * W + w] = 0;
     }
-    if (clique_start < 0) clique_start = n - 1;
-    int nt = n - clique_start;
-    nt = ((nt + 15) / 16) * 16;
-    nt = std::max(16, std::min(nt, n));
-    // the Schur complement (nt*nt) plus one dense work row per warp (8 warps) must fit
-    // the integrator's shared memory next to its 12 length-n vectors (racg_integrate.cu)
-    {
-      const double budget = 227.0 * 1024 - 8.0 * (12.0 * n + 64) - 8.0 * 8 * n - 2048;
-      int cap = (int)std::floor(std::sqrt(std::max(budget, 0.0) / 8.0));
-      cap = (cap / 16) * 16;
-      if (cap < 16) { hn.error = "network too large for the integrator's shared-memory layout"; return false; }
-      nt = std::min(nt, cap);
+    return order;
+  };
+  // symbolic LU of the permuted pattern for a given order -> F (bitset rows)
+  auto symbolic = [&](const std::vector<int>& perm, std::vector<uint64_t>& F) {
+    F.assign((size_t)n * W, 0);
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) if (getb(A, perm[r], perm[c])) setb(F, r, c);
+    for (int i = 0; i < n; ++i) {
+      uint64_t* fi = &F[(size_t)i * W];
+      for (int k = 0; k < i; ++k) {
+        if (!((fi[k >> 6] >> (k & 63)) & 1ull)) continue;
+        const uint64_t* fk = &F[(size_t)k * W];
+        for (int w = (k >> 6); w < W; ++w) {
+          uint64_t m = fk[w];
+          if (w == (k >> 6)) m &= ~((2ull << (k & 63)) - 1ull);
+          fi[w] |= m;
+        }
+      }
     }
+  };
+  int clique_start = -1;
+  std::vector<int> order0 = min_degree_order(1.0, 0, &clique_start);
+  if (clique_start < 0) clique_start = n - 1;
+  int nt0 = ((n - clique_start + 15) / 16) * 16;
+  nt0 = std::max(16, std::min(std::min(nt0, 128), (n / 16) * 16));
+  std::vector<uint64_t> F;
+  const size_t smem_budget = 227 * 1024 - 2048;
+  bool placed = false;
+  for (int nt = nt0; nt >= 16 && !placed; nt -= 16) {
     hn.nt = nt; hn.nh = n - nt;
+    hn.perm = min_degree_order(1.5, hn.nh, nullptr);
+    symbolic(hn.perm, F);
+    int n_hh = 0;
+    for (int i = 0; i < hn.nh; ++i) for (int c = 0; c < hn.nh; ++c) if (getb(F, i, c) || c == i) ++n_hh;
+    // minimum shared memory of the integrator (racg_integrate.cu make_layout): 2 length-n
+    // vectors + 1/pivots + tail (ld = nt+1) + scratch; the head x head block and the
+    // factorisation's U_B copy go to the L2 workspace when they do not fit as well
+    (void)n_hh;
+    size_t scratch = std::max<size_t>((size_t)R + 2048, (size_t)8 * n);
+    size_t need = 8 * ((size_t)2 * n + hn.nh + 64 + (size_t)(nt + 1) * nt + scratch);
+    if (need <= smem_budget) placed = true;
   }
-  // ---- symbolic LU on the permuted pattern (row merge; no pivoting)
-  std::vector<uint64_t> F((size_t)n * W, 0);
-  for (int r = 0; r < n; ++r)
-    for (int c = 0; c < n; ++c) if (getb(A, hn.perm[r], hn.perm[c])) setb(F, r, c);
-  for (int i = 0; i < n; ++i) {
-    uint64_t* fi = &F[(size_t)i * W];
-    for (int k = 0; k < i; ++k) {
-      if (!((fi[k >> 6] >> (k & 63)) & 1ull)) continue;
-      const uint64_t* fk = &F[(size_t)k * W];
-      // merge the U part of row k (cols > k)
-      for (int w = (k >> 6); w < W; ++w) {
-        uint64_t m = fk[w];
-        if (w == (k >> 6)) m &= ~((2ull << (k & 63)) - 1ull);
-        fi[w] |= m;
-      }
-    }
-  }
+  if (!placed) { hn.error = "network too large for the integrator's shared-memory layout"; return false; }
   const int nh = hn.nh, nt = hn.nt;
+  hn.iperm.assign(n, 0);
+  for (int i = 0; i < n; ++i) hn.iperm[hn.perm[i]] = i;
   hn.nnz_lu = 0;
   for (int i = 0; i < n; ++i) for (int w = 0; w < W; ++w) hn.nnz_lu += __builtin_popcountll(F[(size_t)i * W + w]);
-  hn.row_ptr.assign(n + 1, 0); hn.row_nl.assign(n, 0); hn.col.clear();
-  for (int i = 0; i < n; ++i) {
+  // ---- storage layout shared by the Jacobian (J) and factor (LU) value arrays
+  // head rows: [L_A | diag | U_A] (hh, resident in shared memory) and U_B (head rows x tail
+  // columns, CSR; in shared memory only while the matrix is being factorised)
+  hn.hh_ptr.assign(nh + 1, 0); hn.hh_nl.assign(nh, 0); hn.hh_col.clear();
+  hn.ub_ptr.assign(nh + 1, 0); hn.ub_col.clear();
+  hn.lc_ptr.assign(nt + 1, 0); hn.lc_col.clear();
+  for (int i = 0; i < nh; ++i) {
     int nl = 0;
-    int cmax = (i < nh) ? n : nh;   // tail rows keep only the L_C part (cols < nh) in CSR
-    for (int c = 0; c < cmax; ++c) {
-      if (!getb(F, i, c) && c != i) continue;
-      hn.col.push_back((uint16_t)c);
-      if (c < i) ++nl;
-    }
-    hn.row_nl[i] = nl;
-    hn.row_ptr[i + 1] = (int)hn.col.size();
+    for (int c = 0; c < nh; ++c) if (getb(F, i, c) || c == i) { hn.hh_col.push_back((uint16_t)c); if (c < i) ++nl; }
+    hn.hh_nl[i] = nl; hn.hh_ptr[i + 1] = (int)hn.hh_col.size();
+    for (int c = nh; c < n; ++c) if (getb(F, i, c)) hn.ub_col.push_back((uint16_t)(c - nh));
+    hn.ub_ptr[i + 1] = (int)hn.ub_col.size();
   }
-  hn.nslots = (int)hn.col.size();
-  // levels
+  for (int a = 0; a < nt; ++a) {
+    for (int c = 0; c < nh; ++c) if (getb(F, nh + a, c)) hn.lc_col.push_back((uint16_t)c);
+    hn.lc_ptr[a + 1] = (int)hn.lc_col.size();
+  }
+  hn.n_hh = (int)hn.hh_col.size(); hn.n_ub = (int)hn.ub_col.size(); hn.n_lc = (int)hn.lc_col.size();
+  hn.ldt = nt + 1;
+  hn.o_ub = hn.n_hh; hn.o_lc = hn.o_ub + hn.n_ub; hn.o_tl = hn.o_lc + hn.n_lc;
+  hn.nstore = hn.o_tl + hn.ldt * nt;
+  // ELL copies of U_B and L_C for the solve's SpMV passes
+  auto build_ell = [&](const std::vector<int>& ptr, const std::vector<uint16_t>& col, int nrows, HostNet::Ell& e,
+                       std::vector<int>& ellpos) {
+    std::vector<std::vector<std::pair<int, int>>> rows(nrows);
+    for (int i = 0; i < nrows; ++i) for (int q = ptr[i]; q < ptr[i + 1]; ++q) rows[i].push_back({q, 0});
+    Gather g;
+    build_gather(g, rows, 32);
+    e.nblk = g.nblk; e.npartial = g.npartial; e.ncombine = g.ncombine;
+    e.blk_off = g.blk_off; e.blk_width = g.blk_width; e.sub_target = g.sub_target;
+    e.comb_row = g.comb_row; e.comb_ptr = g.comb_ptr;
+    e.nval = (int)g.ent.size();
+    e.col.assign(g.ent.size(), 0);
+    ellpos.assign(col.size(), -1);
+    // padding entries were created with idx 0 / coef code 4; real entries carry coef code 4 too
+    // (coef 0), so mark real ones through a second pass
+    std::vector<char> real(g.ent.size(), 0);
+    {
+      // re-derive positions exactly as build_gather laid them out
+      struct Sub { int row, first, len; };
+      std::vector<Sub> subs;
+      for (int r = 0; r < nrows; ++r) {
+        int len = (int)rows[r].size();
+        for (int f = 0; f < len; f += 32) subs.push_back({r, f, std::min(32, len - f)});
+      }
+      std::stable_sort(subs.begin(), subs.end(), [](const Sub& x, const Sub& y) { return x.len > y.len; });
+      for (size_t s = 0; s < subs.size(); ++s) {
+        int b = (int)(s / 32), l = (int)(s % 32);
+        for (int j = 0; j < subs[s].len; ++j) {
+          size_t pos = (size_t)g.blk_off[b] + (size_t)j * 32 + l;
+          int q = rows[subs[s].row][subs[s].first + j].first;
+          e.col[pos] = col[q];
+          ellpos[q] = (int)pos;
+          real[pos] = 1;
+        }
+      }
+    }
+  };
+  build_ell(hn.ub_ptr, hn.ub_col, nh, hn.ubE, hn.ub_ellpos);
+  build_ell(hn.lc_ptr, hn.lc_col, nt, hn.lcE, hn.lc_ellpos);
+  // levels over head rows: forward (L_A dependencies) and backward (U_A dependencies)
   auto make_levels = [&](const std::vector<int>& lev, int count, std::vector<int>& ptr, std::vector<int>& rows) {
     int nlev = 0;
     for (int i = 0; i < count; ++i) nlev = std::max(nlev, lev[i] + 1);
@@ -321,38 +403,70 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     std::vector<int> pos(ptr.begin(), ptr.end() - 1);
     for (int i = 0; i < count; ++i) rows[pos[lev[i]]++] = i;
   };
+  auto first_thin = [&](const std::vector<int>& ptr) {
+    int nlev = (int)ptr.size() - 1, f = nlev;
+    while (f > 0 && ptr[f] - ptr[f - 1] <= 32) --f;
+    return f;   // levels [f, nlev) all have <= 32 rows
+  };
   {
     std::vector<int> lev(nh, 0);
     for (int i = 0; i < nh; ++i) {
       int l = 0;
-      for (int q = hn.row_ptr[i]; q < hn.row_ptr[i] + hn.row_nl[i]; ++q) l = std::max(l, lev[hn.col[q]] + 1);
+      for (int q = hn.hh_ptr[i]; q < hn.hh_ptr[i] + hn.hh_nl[i]; ++q) l = std::max(l, lev[hn.hh_col[q]] + 1);
       lev[i] = l;
     }
     make_levels(lev, nh, hn.flev_ptr, hn.flev_rows);
-    hn.sl_ptr = hn.flev_ptr; hn.sl_rows = hn.flev_rows;
+    hn.head_level = lev;
+    hn.nfat_f = first_thin(hn.flev_ptr);
     std::vector<int> levu(nh, 0);
     for (int i = nh - 1; i >= 0; --i) {
       int l = 0;
-      for (int q = hn.row_ptr[i] + hn.row_nl[i] + 1; q < hn.row_ptr[i + 1]; ++q) {
-        int c = hn.col[q];
-        if (c < nh) l = std::max(l, levu[c] + 1);
-      }
+      for (int q = hn.hh_ptr[i] + hn.hh_nl[i] + 1; q < hn.hh_ptr[i + 1]; ++q) l = std::max(l, levu[hn.hh_col[q]] + 1);
       levu[i] = l;
     }
     make_levels(levu, nh, hn.su_ptr, hn.su_rows);
+    hn.nfat_b = first_thin(hn.su_ptr);
   }
+  hn.pivmeta.assign((size_t)4 * nh, 0); hn.fmeta.assign((size_t)4 * nh, 0); hn.bmeta.assign((size_t)4 * nh, 0);
+  for (int k = 0; k < nh; ++k) {
+    hn.pivmeta[4 * k + 0] = hn.hh_ptr[k] + hn.hh_nl[k] + 1;                       // start of U_A(k,:) in hh
+    hn.pivmeta[4 * k + 1] = hn.hh_ptr[k + 1] - (hn.hh_ptr[k] + hn.hh_nl[k] + 1);    // its length
+    hn.pivmeta[4 * k + 2] = hn.ub_ptr[k];                                           // start of U_B(k,:)
+    hn.pivmeta[4 * k + 3] = hn.ub_ptr[k + 1] - hn.ub_ptr[k];                        // its length
+  }
+  for (int p = 0; p < nh; ++p) {
+    int i = hn.flev_rows[p];
+    hn.fmeta[4 * p + 0] = i; hn.fmeta[4 * p + 1] = hn.hh_ptr[i]; hn.fmeta[4 * p + 2] = hn.hh_nl[i];
+    i = hn.su_rows[p];
+    hn.bmeta[4 * p + 0] = i; hn.bmeta[4 * p + 1] = hn.hh_ptr[i] + hn.hh_nl[i] + 1;
+    hn.bmeta[4 * p + 2] = hn.hh_ptr[i + 1] - (hn.hh_ptr[i] + hn.hh_nl[i] + 1);
+  }
+  // tail rows in decreasing L_C length (longest first) for the Schur phase
+  hn.tail_order.resize(nt);
+  std::iota(hn.tail_order.begin(), hn.tail_order.end(), 0);
+  std::stable_sort(hn.tail_order.begin(), hn.tail_order.end(), [&](int x, int y) {
+    return hn.lc_ptr[x + 1] - hn.lc_ptr[x] > hn.lc_ptr[y + 1] - hn.lc_ptr[y]; });
 
   // ---- Jacobian gather: J(i,j) = sum_r coef_i(r) * dflux[r][which(j)]  (src/disk.f90:4765-4875)
-  // storage index of (pi,pj) in permuted space
   auto store_index = [&](int pi, int pj) -> int {
-    if (pi >= nh && pj >= nh) return hn.nslots + (pi - nh) * nt + (pj - nh);
-    int lo = hn.row_ptr[pi], hi = hn.row_ptr[pi + 1];
-    auto it = std::lower_bound(hn.col.begin() + lo, hn.col.begin() + hi, (uint16_t)pj);
-    if (it == hn.col.begin() + hi || *it != pj) return -1;
-    return (int)(it - hn.col.begin());
+    if (pi >= nh && pj >= nh) return hn.o_tl + (pj - nh) * hn.ldt + (pi - nh);
+    if (pi < nh && pj < nh) {
+      auto lo = hn.hh_col.begin() + hn.hh_ptr[pi], hi = hn.hh_col.begin() + hn.hh_ptr[pi + 1];
+      auto it = std::lower_bound(lo, hi, (uint16_t)pj);
+      return (it == hi || *it != pj) ? -1 : (int)(it - hn.hh_col.begin());
+    }
+    if (pi < nh) {
+      auto lo = hn.ub_col.begin() + hn.ub_ptr[pi], hi = hn.ub_col.begin() + hn.ub_ptr[pi + 1];
+      auto it = std::lower_bound(lo, hi, (uint16_t)(pj - nh));
+      return (it == hi || *it != pj - nh) ? -1 : hn.o_ub + (int)(it - hn.ub_col.begin());
+    }
+    auto lo = hn.lc_col.begin() + hn.lc_ptr[pi - nh], hi = hn.lc_col.begin() + hn.lc_ptr[pi - nh + 1];
+    auto it = std::lower_bound(lo, hi, (uint16_t)pj);
+    return (it == hi || *it != pj) ? -1 : hn.o_lc + (int)(it - hn.lc_col.begin());
   };
   {
-    std::map<int, std::vector<std::pair<int, int>>> tgt;   // store idx -> (r*2+which, coef)
+    // two passes so that one R-sized scratch suffices: pass q uses d(flux)/d(y_rq)
+    std::map<int, std::vector<std::pair<int, int>>> tgt[2];   // store idx -> (r, coef)
     for (int i = 0; i < R; ++i) {
       uint32_t w = hn.fw[i];
       int kind = (w >> 20) & 3;
@@ -368,38 +482,35 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
           if (kv.second == 0) continue;
           int s = store_index(hn.iperm[kv.first], hn.iperm[j]);
           if (s < 0) { hn.error = "internal: Jacobian entry outside the symbolic pattern"; return false; }
-          tgt[s].push_back({i * 2 + q, kv.second});
+          tgt[q][s].push_back({i, kv.second});
         }
       }
     }
-    std::vector<std::vector<std::pair<int, int>>> rows;
-    std::vector<int> row_store;
-    for (auto& kv : tgt) { row_store.push_back(kv.first); rows.push_back(kv.second); }
-    build_gather(hn.jac, rows, 32);
-    // translate row ids to store indices
-    for (auto& t : hn.jac.sub_target) if (t >= 0) t = row_store[t];
-    for (auto& r : hn.jac.comb_row) r = row_store[r];
-  }
-  // CSC slot -> storage index (species block only; T row/col are identically zero for evolT=F)
-  hn.csc_to_store.assign(hn.NNZ, -1);
-  hn.rx_slots.assign((size_t)12 * R, -1);
-  {
-    std::vector<int> slot_of((size_t)NEQ * NEQ, -1);
-    for (int c = 0; c < NEQ; ++c)
-      for (int k = hn.ia[c] - 1; k < hn.ia[c + 1] - 1; ++k) {
-        int r = hn.ja[k] - 1;
-        slot_of[(size_t)c * NEQ + r] = k;
-        if (r < n && c < n) hn.csc_to_store[k] = store_index(hn.iperm[r], hn.iperm[c]);
-      }
-    for (int i = 0; i < R; ++i) {
-      const int* sp = &hn.rx_species[(size_t)6 * i];
-      for (int q = 0; q < 2; ++q) {
-        if (sp[q] < 0) continue;
-        for (int k = 0; k < 6; ++k)
-          if (sp[k] >= 0) hn.rx_slots[(size_t)12 * i + 6 * q + k] = slot_of[(size_t)sp[q] * NEQ + sp[k]];
+    for (int q = 0; q < 2; ++q) {
+      std::vector<std::vector<std::pair<int, int>>> rows;
+      std::vector<int> row_store;
+      for (auto& kv : tgt[q]) { row_store.push_back(kv.first); rows.push_back(kv.second); }
+      Gather& g = hn.jac[q];
+      build_gather(g, rows, 32);
+      for (auto& t : g.sub_target) if (t >= 0) t = row_store[t];
+      for (auto& r : g.comb_row) r = row_store[r];
+      // pass 1 adds to what pass 0 stored; targets untouched by pass 0 are stored
+      g.sub_add.assign(g.sub_target.size(), 0);
+      g.comb_add.assign(g.comb_row.size(), 0);
+      if (q == 1) {
+        for (size_t k = 0; k < g.sub_target.size(); ++k)
+          if (g.sub_target[k] >= 0 && tgt[0].count(g.sub_target[k])) g.sub_add[k] = 1;
+        for (size_t k = 0; k < g.comb_row.size(); ++k) if (tgt[0].count(g.comb_row[k])) g.comb_add[k] = 1;
       }
     }
   }
+  // CSC slot -> storage index (species block only; T row/col are identically zero for evolT=F)
+  hn.csc_to_store.assign(hn.NNZ, -1);
+  for (int c = 0; c < n; ++c)
+    for (int k = hn.ia[c] - 1; k < hn.ia[c + 1] - 1; ++k) {
+      int r = hn.ja[k] - 1;
+      if (r < n) hn.csc_to_store[k] = store_index(hn.iperm[r], hn.iperm[c]);
+    }
   // ---- stand-alone K3 schedule: columns grouped so that a group's partial
   // derivatives fit the shared-memory buffer; hub columns are cut into chunks that
   // accumulate into pd.

@@ -35,6 +35,7 @@ struct Gather {
   std::vector<uint32_t> ent;       // idx | (coef+4)<<24   (idx < 2^24)
   std::vector<int> comb_row;       // [ncombine] rows that own several sub-rows
   std::vector<int> comb_ptr;       // [ncombine+1] into partial ids (consecutive ids)
+  std::vector<uint8_t> sub_add, comb_add;  // optional: 1 = add to the target instead of storing
   long nent_real = 0;
 };
 
@@ -68,23 +69,38 @@ struct HostNet {
   int n = 0;                      // = N
   int nh = 0, nt = 0;             // head (sparse) / tail (dense) split, nh + nt = n
   std::vector<int> perm, iperm;   // permuted -> original species (0-based), inverse
-  // head rows i < nh : CSR  [L_A | diag | U_A U_B], tail rows: CSR of L_C only
-  std::vector<int> row_ptr;       // [n+1] into col/val slots ("LU slots")
-  std::vector<int> row_nl;        // [n] number of L entries of the row (tail rows: all)
-  std::vector<uint16_t> col;      // [nslots] permuted column ids
-  int nslots = 0;                 // sparse LU slots (head rows + L_C)
-  int nnz_lu = 0;                 // nnz(L+D+U) of the whole pattern (tail counted by its pattern)
-  // levels
-  std::vector<int> flev_ptr, flev_rows;   // head factorisation levels (rows < nh)
-  std::vector<int> sl_ptr, sl_rows;       // forward-solve levels over head rows
-  std::vector<int> su_ptr, su_rows;       // backward-solve levels over head rows
-  // ---- Jacobian gather into: sparse LU slots [0,nslots) and dense tail nslots + a*nt + b ----
-  Gather jac;
-  // map from the user's CSC slot (ia/ja) to the J storage index (for racg_rhs_jac parity) or -1
+  int nnz_lu = 0;                 // nnz(L+D+U) of the symbolic factorisation
+  // value-storage index space shared by J and LU:
+  //   [0,n_hh)        head x head block, CSR by head row: [L_A | diag | U_A]
+  //   [o_ub,+n_ub)    U_B: head rows x tail columns, CSR
+  //   [o_lc,+n_lc)    L_C: tail rows x head columns, CSR
+  //   [o_tl,+ldt*nt)  dense tail block, column-major, leading dimension ldt
+  int n_hh = 0, n_ub = 0, n_lc = 0, o_ub = 0, o_lc = 0, o_tl = 0, ldt = 0, nstore = 0;
+  std::vector<int> hh_ptr, hh_nl; std::vector<uint16_t> hh_col;
+  std::vector<int> ub_ptr; std::vector<uint16_t> ub_col;   // tail-local column
+  std::vector<int> lc_ptr; std::vector<uint16_t> lc_col;   // head column
+  // ELL (32 sub-rows per block, transposed) copies of U_B / L_C for the solve passes
+  struct Ell {
+    int nblk = 0, npartial = 0, ncombine = 0, nval = 0;
+    std::vector<int> blk_off, blk_width, sub_target, comb_row, comb_ptr;
+    std::vector<uint16_t> col;
+  } ubE, lcE;
+  std::vector<int> ub_ellpos, lc_ellpos;     // CSR slot -> ELL position
+  // levels over head rows
+  std::vector<int> flev_ptr, flev_rows, head_level;   // forward / factorisation (L_A)
+  std::vector<int> su_ptr, su_rows;                   // backward (U_A)
+  int nfat_f = 0, nfat_b = 0;     // levels >= nfat have <= 32 rows (handled by one warp)
+  std::vector<int> tail_order;    // tail rows, longest L_C row first
+  // packed metadata (int4 each) so that the sparse phases never chase pointers:
+  //   pivmeta[k]  = {start of U_A(k,:) in hh, its length, start of U_B(k,:), its length}
+  //   fmeta[pos]  = {row, start of L_A(row,:) in hh, its length, 0}   in forward-level order
+  //   bmeta[pos]  = {row, start of U_A(row,:) in hh, its length, 0}   in backward-level order
+  std::vector<int> pivmeta, fmeta, bmeta;
+  // ---- Jacobian gather into the storage index space, two passes (d/dy_r1, d/dy_r2) ----
+  Gather jac[2];
+  // map from the user's CSC slot (ia/ja) to the storage index or -1
   std::vector<int> csc_to_store;
-  // standalone K2/K3 tables: per reaction (r1,r2,p[4] 0-based or -1, kind) and CSC slots
   std::vector<int> rx_species;    // [6*R] r1,r2,p1..p4 (0-based, -1 none)
-  std::vector<int> rx_slots;      // [12*R] CSC slot of (participant k, reactant q) or -1
   // ---- stand-alone K3 (column-group schedule, see racg_batch.cu) ----
   struct JacCols {
     int ngroups = 0, max_pairs = 0;

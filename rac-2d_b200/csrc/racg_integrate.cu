@@ -1,19 +1,25 @@
 // racg_integrate.cu -- the persistent per-cell stiff integrator of libracg (sm_100a).
 //
-// One CTA integrates one grid cell at a time (north_star (c)); a persistent grid
-// pulls cells from an atomic work queue (K7) so that cells of very different
-// stiffness balance.  All length-N vectors of the BDF controller live in shared
-// memory; the Jacobian and the LU factors of the cell live in a per-CTA workspace
-// that stays L2-resident.  What it restates, per cell, is the reference's
+// One CTA (256 threads) integrates one grid cell at a time (north_star (c)); a
+// persistent grid of one CTA per SM pulls cells from an atomic work queue (K7) so that
+// cells of very different stiffness balance.  What it restates, per cell, is the
+// reference's
 //   chem_evol_solve loop            src/chemistry.f90:391-588
 //   DLSODES driver (MF=21, ITASK=4) src/opkdmain.f:3069-3588
 //   DSTODE / DPRJS / DSOLSS         src/opkda1.f:629-1126, 1664-1942
 //   DEWSET / DVNORM / DINTDY        src/opkda1.f:1127-1209, 174-281
 //   chem_ode_f / chem_ode_jac       src/disk.f90:4569-4659, 4746-4903 (evolT=.false.)
 //   chem_cal_rates                  src/chemistry.f90:591-966
-// with YSMP's sparse LU replaced by a fixed-pattern LU on the host-computed
-// ordering: sparse "head" rows eliminated level by level (one warp per row) and a
-// dense "tail" Schur complement factorised in shared memory.
+// with YSMP's sparse LU replaced by a fixed-pattern LU on the host-computed ordering.
+//
+// Data placement (per cell):
+//   registers      Nordsieck array YH (6 columns), ACOR, EWT, RTOL/ATOL: element i of every
+//                  vector lives in thread i mod 256 (all controller updates are elementwise)
+//   shared memory  y / savf / solve vector / 1/pivots, the dense "tail" block of the LU
+//                  (Schur complement of the hub species), the head x head block of the LU,
+//                  and a scratch region (reaction fluxes | factorisation work rows + U_B)
+//   L2-resident    per-CTA workspace: Jacobian in LU-slot order, ELL copies of the two
+//                  coupling blocks U_B / L_C for the solves, the cell's rate coefficients
 #include <cuda_runtime.h>
 #include <cstdio>
 #include "racg_dev.cuh"
@@ -21,24 +27,84 @@
 
 namespace racg {
 
-constexpr int NT = 256;           // threads per CTA
+constexpr int NT = 256;           // threads per CTA (16 x 16 grid for the dense tail LU)
 constexpr int NW = NT / 32;       // warps per CTA
+constexpr int MAXTL = 8;          // tail tile edge per thread: nt <= 16 * MAXTL = 128
 
 enum Phase { PH_RATES = 0, PH_F, PH_JAC, PH_FACT_HEAD, PH_FACT_SCHUR, PH_FACT_TAIL, PH_SOLVE,
-             PH_VEC, PH_IO, PH_TOTAL, PH_NCELL, PH_COUNT };
+             PH_VEC, PH_IO, PH_TOTAL, PH_NCELL, PH_PBUILD, PH_TAILINV, PH_COUNT };
 
 struct Smem {
-  double* yh;     // [6][n]
-  double* y;      // [n]
-  double* savf;   // [n]
-  double* acor;   // [n]
-  double* ewt;    // [n]
-  double* xb;     // [n]  solve vector (permuted space)
-  double* dinv;   // [n]
+  double* y;      // [n]  argument of f / right-hand side and result of the linear solve
+  double* savf;   // [n]  f(y)
+  double* xb;     // solve vector in elimination order: aliases savf (dead while P x = b is solved)
+  double* dinv;   // [nh] 1 / pivot of the head rows
   double* par;    // [32]
-  double* red;    // [NW*2]
-  double* X;      // overlay region
+  double* red;    // [2*NW]
+  double* Dt;     // [ldt*nt] dense tail, column-major; diagonal 32-blocks hold their inverses
+  double* hh;     // [n_hh] head x head block (shared memory, or workspace when it does not fit)
+  double* X;      // scratch
+  // read-only index tables staged once per CTA (they sit on dependent-load chains)
+  const uint16_t* hhcol;   // [n_hh]
+  const int4* fthin;       // forward thin-level rows {row, start, len, 0}
+  const int4* bthin;       // backward thin-level rows
+  const int* flptr;        // [nflev+1] forward level pointers
+  const int* suptr;        // [nsu+1] backward level pointers
 };
+
+struct Ws {          // per-CTA global workspace (L2 resident)
+  double* J;         // [nstore] Jacobian in storage order
+  double* ubE;       // [ubE.nval] U_B values, ELL order
+  double* lcE;       // [lcE.nval] L_C values, ELL order
+  double* ksave;     // [R] rate coefficients of the cell
+  double* hhG;       // [n_hh] fallback home of hh
+  double* ubG;       // [n_ub] fallback home of the factorisation's U_B
+};
+
+struct Layout { int hh_smem, ub_smem, nwr; size_t xdoubles, total; };
+
+// network descriptor in constant memory: every device function reads it through the
+// constant cache (passing the ~1 KB struct by reference would spill it to local memory)
+__constant__ DevNet c_net;
+
+// Shared-memory plan.  Preferred: everything (head x head block, the factorisation's copy
+// of U_B) on chip AND the total under 196 KB, so that the SM keeps >= 60 KB of L1 for the
+// read-only index tables the sparse phases chase (they sit on dependent-load chains: at L2
+// latency they dominated the first version of this kernel).  nwr = number of warps that
+// own a dense work row during the row phases of the factorisation.
+__host__ __device__ inline Layout make_layout(const DevNet& net) {
+  Layout L;
+  const size_t n = net.n, R = net.R;
+  const size_t nthin_f = (size_t)(net.nh - net.flev_nfat_rows), nthin_b = (size_t)(net.nh - net.su_nfat_rows);
+  const size_t tables = ((size_t)net.n_hh * 2 + (nthin_f + nthin_b) * 16 +
+                         (size_t)(net.nflev + net.nsu + 2) * 4 + 64 + 7) / 8;
+  const size_t fixed = 2 * n + net.nh + 32 + 2 * NW + (size_t)net.ldt * net.nt + tables;
+  // scratch X: fluxes + gather partials | dflux + partials | SpMV partials | tolerance staging |
+  // tail_lu publication buffers; during the factorisation: nwr work rows + U_B values + U_B columns
+  size_t x_f = R + (size_t)net.rhs.npartial + 32;
+  const size_t xj0 = R + (size_t)net.jac[0].npartial + 32, xj1 = R + (size_t)net.jac[1].npartial + 32;
+  if (xj0 > x_f) x_f = xj0;
+  if (xj1 > x_f) x_f = xj1;
+  const size_t xs = (size_t)net.ubE.npartial + (size_t)net.lcE.npartial + 32;
+  if (xs > x_f) x_f = xs;
+  if (2 * n > x_f) x_f = 2 * n;
+  if (600 > x_f) x_f = 600;
+  const size_t ubx = (size_t)net.n_ub + ((size_t)net.n_ub * 2 + 7) / 8 + 2;   // values + u16 columns
+  const size_t big = (227 * 1024 - 1024) / 8;
+  L.hh_smem = 1; L.ub_smem = 1; L.nwr = NW;
+  bool ok = false;
+  for (int nwr = NW; nwr >= 4 && !ok; --nwr) {
+    size_t x = (size_t)nwr * n + ubx;
+    if (x < x_f) x = x_f;
+    if (fixed + net.n_hh + x <= big) { L.nwr = nwr; ok = true; }
+  }
+  if (!ok) { L.nwr = NW; L.hh_smem = 0; L.ub_smem = 0; }   // large networks: L2 workspace
+  size_t x = (size_t)L.nwr * n + (L.ub_smem ? ubx : 0);
+  if (x < x_f) x = x_f;
+  L.xdoubles = x;
+  L.total = fixed + (L.hh_smem ? net.n_hh : 0) + x;
+  return L;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -59,16 +125,21 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
-// DVNORM over the species (the T slot contributes 0 to every vector we norm except
-// YH(:,1); N in the denominator is NEQ as in the reference)
-__device__ __forceinline__ double wrms(const double* v, const double* w, int n, int NEQ, double* red) {
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += NT) { double a = v[i] * w[i]; s += a * a; }
-  return sqrt(block_sum(s, red) / (double)NEQ);
+__device__ __forceinline__ double block_max(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = red[0];
+#pragma unroll
+  for (int k = 1; k < NW; ++k) s = fmax(s, red[k]);
+  return s;
 }
 
 // ---------------------------------------------------------------------------
-// generic segmented-ELL gather: out[target] = sum coef * src[idx]
+// segmented-ELL gather: out[target] (+)= sum coef * src[idx]; all index loads of a
+// block are issued before the first use (one L2 round trip per block)
 template <bool GLOBAL_OUT>
 __device__ __forceinline__ void run_gather(const GatherDev& g, const double* src, double* out,
                                            double* partial) {
@@ -76,28 +147,34 @@ __device__ __forceinline__ void run_gather(const GatherDev& g, const double* src
   for (int b = w; b < g.nblk; b += NW) {
     const int off = g.blk_off[b], width = g.blk_width[b];
     const uint32_t* e = g.ent + off + l;
+    uint32_t ev[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ev[j] = (j < width) ? __ldcs(e + j * 32) : (4u << 24);
     double acc = 0.0;
-    for (int j = 0; j < width; ++j) {
-      const uint32_t v = __ldg(e + j * 32);
-      const int c = (int)(v >> 24) - 4;
-      const double s = src[v & 0xffffffu];
-      acc += (c != 0) ? (double)c * s : 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < width) {
+        const int c = (int)(ev[j] >> 24) - 4;
+        const double s = src[ev[j] & 0xffffffu];
+        acc += (c != 0) ? (double)c * s : 0.0;
+      }
     }
     const int t = g.sub_target[b * 32 + l];
-    if (t >= 0) out[t] = acc;
-    else if (t <= -2) partial[-2 - t] = acc;
+    if (t >= 0) {
+      if (GLOBAL_OUT && g.sub_add && g.sub_add[b * 32 + l]) out[t] += acc; else out[t] = acc;
+    } else if (t <= -2) partial[-2 - t] = acc;
   }
   __syncthreads();
   for (int q = threadIdx.x; q < g.ncombine; q += NT) {
     double s = 0.0;
     for (int p = g.comb_ptr[q]; p < g.comb_ptr[q + 1]; ++p) s += partial[p];
-    out[g.comb_row[q]] = s;
+    if (GLOBAL_OUT && g.comb_add && g.comb_add[q]) out[g.comb_row[q]] += s; else out[g.comb_row[q]] = s;
   }
   __syncthreads();
 }
 
 // flux of reaction r (branches of chem_ode_f, src/disk.f90:4583-4643)
-__device__ __forceinline__ double flux_of(const DevNet& net, uint32_t w, double k, const double* y,
+__device__ __forceinline__ double flux_of(uint32_t w, double k, const double* y,
                                           double DS) {
   const int kind = (w >> 20) & 3;
   const double y1 = y[w & 1023];
@@ -109,7 +186,7 @@ __device__ __forceinline__ double flux_of(const DevNet& net, uint32_t w, double 
     return r;
   }
   if (kind == FK_SAT) {
-    const double tmp1 = DS * net.sat_c[w >> 22];
+    const double tmp1 = DS * c_net.sat_c[w >> 22];
     if (tmp1 <= 0.0) return k;
     const double tmp = y1 / tmp1;
     return (tmp <= 1e-4) ? k * tmp : k * (1.0 - exp(-tmp));
@@ -117,219 +194,491 @@ __device__ __forceinline__ double flux_of(const DevNet& net, uint32_t w, double 
   return 0.0;
 }
 
-// d flux / d y(r1) and d flux / d y(r2) (branches of chem_ode_jac, src/disk.f90:4765-4866)
-__device__ __forceinline__ void dflux_of(const DevNet& net, uint32_t w, double k, const double* y,
-                                         double DS, double& d0, double& d1) {
+// d flux / d y(r1) (which = 0) or d flux / d y(r2) (which = 1)
+// (branches of chem_ode_jac, src/disk.f90:4765-4866)
+__device__ __forceinline__ double dflux_of(uint32_t w, double k, const double* y,
+                                           double DS, int which) {
   const int kind = (w >> 20) & 3;
   const int r1 = w & 1023, r2 = (w >> 10) & 1023;
-  d0 = 0.0; d1 = 0.0;
-  if (kind == FK_ONE) { d0 = k; return; }
+  if (kind == FK_ONE) return which == 0 ? k : 0.0;
   if (kind == FK_TWO) {
     const double y1 = y[r1], y2 = y[r2];
-    const bool flip = (y1 < 0.0 && y2 < 0.0);
-    if (r1 != r2) { d0 = k * y2; d1 = k * y1; }
-    else d0 = 2.0 * k * y2;
-    if (flip) { d0 = -d0; d1 = -d1; }
-    return;
+    double d;
+    if (r1 != r2) d = (which == 0) ? k * y2 : k * y1;
+    else d = (which == 0) ? 2.0 * k * y2 : 0.0;
+    if (y1 < 0.0 && y2 < 0.0) d = -d;
+    return d;
   }
   if (kind == FK_SAT) {
-    const double tmp2 = DS * net.sat_c[w >> 22];
-    if (tmp2 <= 0.0) { d0 = 0.0; return; }
+    if (which != 0) return 0.0;
+    const double tmp2 = DS * c_net.sat_c[w >> 22];
+    if (tmp2 <= 0.0) return 0.0;
     const double tmp1 = 1.0 / tmp2;
     const double tmp = y[r1] * tmp1;
-    d0 = (tmp <= 1e-4) ? k * tmp1 : k * tmp1 * exp(-tmp);
+    return (tmp <= 1e-4) ? k * tmp1 : k * tmp1 * exp(-tmp);
   }
+  return 0.0;
 }
 
-struct Ws {          // per-CTA global workspace
-  double* J;         // [nJ] Jacobian in storage order (sparse slots, then dense tail row-major)
-  double* LU;        // [nslots] sparse LU values
-  double* Dt;        // [nt*nt] factored tail, column-major
-  double* ksave;     // [R]
-  double* rtol;      // [NEQ]
-  double* atol;      // [NEQ]
-};
-
-// chem_ode_f: out = S * flux(k, yv).  kx = rates in smem, fx = flux scratch, px = partials
-__device__ __forceinline__ void eval_f(const DevNet& net, const double* kx, double* fx, double* px,
-                                       const double* yv, double* out, double DS) {
-  for (int r = threadIdx.x; r < net.R; r += NT) fx[r] = flux_of(net, __ldg(net.fw + r), kx[r], yv, DS);
+// chem_ode_f: out = S * flux(k, yv).  k streamed from the workspace (L2), fluxes in X
+__device__ __forceinline__ void eval_f(const double* __restrict__ ks, double* fx,
+                                       double* px, const double* yv, double* out, double DS) {
+  const DevNet& net = c_net;
+  const int R = net.R;
+  __syncthreads();   // yv was just written by its owner threads
+  for (int r0 = threadIdx.x; r0 < R; r0 += 4 * NT) {
+    double kk[4]; uint32_t ww[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * NT;
+      kk[u] = (r < R) ? __ldcs(ks + r) : 0.0;
+      ww[u] = (r < R) ? __ldg(net.fw + r) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * NT;
+      if (r < R) fx[r] = flux_of(ww[u], kk[u], yv, DS);
+    }
+  }
   for (int i = threadIdx.x; i < net.n; i += NT) out[i] = 0.0;
   __syncthreads();
   run_gather<false>(net.rhs, fx, out, px);
 }
 
-// chem_ode_jac for all columns at once -> ws.J
-__device__ __forceinline__ void eval_jac(const DevNet& net, const double* kx, double* dfx, double* px,
-                                         const double* yv, double* J, double DS) {
-  for (int r = threadIdx.x; r < net.R; r += NT) {
-    double d0, d1;
-    dflux_of(net, __ldg(net.fw + r), kx[r], yv, DS, d0, d1);
-    dfx[2 * r] = d0; dfx[2 * r + 1] = d1;
-  }
+// chem_ode_jac for all columns at once -> ws.J (two passes over the reactions)
+__device__ __forceinline__ void eval_jac(const double* __restrict__ ks, double* dfx,
+                                         double* px, const double* yv, double* J, double DS) {
+  const DevNet& net = c_net;
   __syncthreads();
-  run_gather<true>(net.jac, dfx, J, px);
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int r = threadIdx.x; r < net.R; r += NT) dfx[r] = dflux_of(__ldg(net.fw + r), __ldcs(ks + r), yv, DS, pass);
+    __syncthreads();
+    run_gather<true>(net.jac[pass], dfx, J, px);
+  }
 }
 
-// P = I - hl0*J, numeric LU.  Returns (to all threads) 0 ok / 1 zero pivot.
-__device__ int factor(const DevNet& net, const Ws& ws, Smem& sm, double con, int* flag,
-                      unsigned long long* ph) {
-  const int n = net.n, nh = net.nh, nt = net.nt;
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  double* wrow = sm.X + (size_t)w * n;             // per-warp dense work row
-  double* S = sm.X + (size_t)NW * n;               // [nt][nt] row-major Schur complement
-  if (threadIdx.x == 0) *flag = 0;
+// ---------------------------------------------------------------------------
+// dense no-pivot LU of the nt x nt tail block held in sm.Dt (column-major, ld = ldt),
+// register tiled: thread (ti,tj) of a 16x16 grid owns rows ti+16a, cols tj+16b.
+// One barrier per elimination step: the owners of column k / row k publish the unscaled
+// column, the row and the pivot; everybody scales and updates its tile.
+// helpers with a compile-time tile index so that register arrays stay in registers
+template <int TL, int B> struct PubCol { template <class T> static __device__ __forceinline__ void go(const T& t, double* pc, int ti) {
+#pragma unroll
+  for (int a = 0; a < TL; ++a) pc[ti + 16 * a] = t[a][B]; } };
+template <int TL, int A> struct PubRow { template <class T> static __device__ __forceinline__ void go(const T& t, double* pr, int tj) {
+#pragma unroll
+  for (int b = 0; b < TL; ++b) pr[tj + 16 * b] = t[A][b]; } };
+
+// one elimination step for the tile block row/col KA (uniform across the CTA)
+template <int TL, int KA>
+__device__ __forceinline__ void tail_step(double (&t)[TL][TL], int k, int kr, int ti, int tj, double* pc, double* pr, int* flag) {
+  if (tj == kr) PubCol<TL, KA>::go(t, pc, ti);
+  if (ti == kr) PubRow<TL, KA>::go(t, pr, tj);
   __syncthreads();
-  long long t0 = clock64();
-  auto pval = [&](int slot, bool diag) -> double {   // WK = J*CON (+1 on the diagonal), src/opkda1.f:1763-1764
-    double v = ws.J[slot] * con;
-    if (diag) v = v + 1.0;
-    return v;
-  };
-  // ---- phase 1: head rows, level by level, one warp per row (up-looking)
-  for (int lev = 0; lev < net.nflev; ++lev) {
-    const int rb = net.flev_ptr[lev], re = net.flev_ptr[lev + 1];
-    for (int ri = rb + w; ri < re; ri += NW) {
-      const int i = net.flev_rows[ri];
-      const int base = net.row_ptr[i], nl = net.row_nl[i], len = net.row_ptr[i + 1] - base;
-      for (int q = l; q < len; q += 32) { const int c = net.col[base + q]; wrow[c] = pval(base + q, c == i); }
-      __syncwarp();
-      for (int q = 0; q < nl; ++q) {
-        const int k = net.col[base + q];
-        const double lv = wrow[k] * sm.dinv[k];
-        if (l == 0) ws.LU[base + q] = lv;
-        const int kb = net.row_ptr[k] + net.row_nl[k] + 1, klen = net.row_ptr[k + 1] - kb;
-        for (int t = l; t < klen; t += 32) wrow[net.col[kb + t]] -= lv * ws.LU[kb + t];
-        __syncwarp();
+  const double piv = pc[k];
+  if (piv == 0.0 || isnan(piv)) { if (threadIdx.x == 0) *flag = 1; }
+  const double inv = 1.0 / piv;
+  // rows a > KA and columns b > KA are fully active, a == KA / b == KA are active for ti > kr / tj > kr
+  double lr[TL], uc[TL];
+#pragma unroll
+  for (int a = KA; a < TL; ++a) lr[a] = pc[ti + 16 * a] * inv;
+#pragma unroll
+  for (int b = KA; b < TL; ++b) uc[b] = pr[tj + 16 * b];
+  const bool rowKA = ti > kr, colKA = tj > kr;
+  if (!rowKA) lr[KA] = 0.0;
+  if (!colKA) uc[KA] = 0.0;
+#pragma unroll
+  for (int a = KA; a < TL; ++a)
+#pragma unroll
+    for (int b = KA; b < TL; ++b) t[a][b] -= lr[a] * uc[b];
+  // column k keeps the multipliers (its uc was zero, so t was untouched above)
+  if (tj == kr) {
+#pragma unroll
+    for (int a = KA + 1; a < TL; ++a) t[a][KA] = lr[a];
+    if (rowKA) t[KA][KA] = lr[KA];
+  }
+}
+
+template <int TL>
+__device__ __noinline__ void tail_lu(Smem sm, double* pub, int* flag) {
+  const DevNet& net = c_net;
+  const int nt = net.nt, ldt = net.ldt;
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  double t[TL][TL];
+#pragma unroll
+  for (int a = 0; a < TL; ++a)
+#pragma unroll
+    for (int b = 0; b < TL; ++b) t[a][b] = sm.Dt[(tj + 16 * b) * ldt + ti + 16 * a];
+  for (int k = 0; k < nt; ++k) {
+    double* pc = pub + (k & 1) * (2 * 128 + 8);
+    double* pr = pc + 128;
+    const int ka = k >> 4, kr = k & 15;
+    switch (ka) {   // uniform across the CTA
+      case 0: tail_step<TL, 0>(t, k, kr, ti, tj, pc, pr, flag); break;
+      case 1: if (TL > 1) tail_step<TL, (TL > 1 ? 1 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
+      case 2: if (TL > 2) tail_step<TL, (TL > 2 ? 2 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
+      case 3: if (TL > 3) tail_step<TL, (TL > 3 ? 3 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
+      case 4: if (TL > 4) tail_step<TL, (TL > 4 ? 4 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
+      case 5: if (TL > 5) tail_step<TL, (TL > 5 ? 5 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
+      case 6: if (TL > 6) tail_step<TL, (TL > 6 ? 6 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
+      default: if (TL > 7) tail_step<TL, (TL > 7 ? 7 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < TL; ++a)
+#pragma unroll
+    for (int b = 0; b < TL; ++b) sm.Dt[(tj + 16 * b) * ldt + ti + 16 * a] = t[a][b];
+  __syncthreads();
+}
+
+// Replace every diagonal 32x32 block of the factored tail by the inverses of its unit-lower
+// and upper triangles (in place), so that the tail substitution becomes a few mat-vecs.
+// One thread per (block, triangle, column), the column of the inverse in registers.
+__device__ __noinline__ void tail_block_inverses(Smem sm) {
+  const DevNet& net = c_net;
+  const int nt = net.nt, ldt = net.ldt, nb = (nt + 31) >> 5;
+  const int job = threadIdx.x >> 5, j = threadIdx.x & 31;     // job = 2*block + (0: L, 1: U)
+  const int blk = job >> 1, upper = job & 1;
+  const int o = blk * 32;
+  const int bs = (nt - o) < 32 ? (nt - o) : 32;
+  const bool act = (job < 2 * nb) && (j < bs);
+  double z[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) z[i] = 0.0;
+  if (act) {
+    const double* D = sm.Dt + (o * ldt + o);
+    if (!upper) {
+      // unit lower: z_j = 1, z_i = -sum_{k=j}^{i-1} L(i,k) z_k
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i == j) z[i] = 1.0;
+        else if (i > j && i < bs) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) if (k < i && k >= j) s += D[k * ldt + i] * z[k];
+          z[i] = -s;
+        }
       }
-      const double d = wrow[i];
+    } else {
+      // upper with diagonal: z_j = 1/U_jj, z_i = -(sum_{k=i+1}^{j} U(i,k) z_k) / U_ii
+#pragma unroll
+      for (int i = 31; i >= 0; --i) {
+        if (i == j) z[i] = 1.0 / D[i * ldt + i];
+        else if (i < j) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) if (k > i && k <= j) s += D[k * ldt + i] * z[k];
+          z[i] = -s / D[i * ldt + i];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (act) {
+    double* D = sm.Dt + (o * ldt + o);
+    if (!upper) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (i > j && i < bs) D[j * ldt + i] = z[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (i <= j) D[j * ldt + i] = z[i];
+    }
+  }
+  __syncthreads();
+}
+
+// P = I - hl0*J (WK = J*CON, +1 on the diagonal; src/opkda1.f:1763-1764) and its numeric LU.
+// Returns (to all threads) 0 ok / 1 zero pivot.
+template <bool ALLSMEM>
+__device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, int* flag, unsigned long long* ph) {
+  const DevNet& net = c_net;
+  const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, tid = threadIdx.x;
+  const int NWR = lay.nwr;
+  double* wrow = sm.X + w * n;                                  // per-warp dense work row
+  // factorisation copy of U_B (CSR values + tail-local columns), in X behind the work rows
+  double* ub = (ALLSMEM || lay.ub_smem) ? sm.X + NWR * n : ws.ubG;
+  const uint16_t* ubcol = (ALLSMEM || lay.ub_smem) ? (const uint16_t*)(sm.X + NWR * n + net.n_ub) : net.ub_col;
+  if (tid == 0) *flag = 0;
+  long long t0 = clock64();
+  // ---- build P
+  for (int s = tid; s < net.n_hh; s += NT) sm.hh[s] = __ldcs(ws.J + s) * con;
+  for (int s = tid; s < net.n_ub; s += NT) ub[s] = __ldcs(ws.J + net.o_ub + s) * con;
+  if (ALLSMEM || lay.ub_smem) {
+    uint16_t* uc = (uint16_t*)(sm.X + NWR * n + net.n_ub);
+    for (int s = tid; s < net.n_ub; s += NT) uc[s] = __ldg(net.ub_col + s);
+  }
+  for (int e = tid; e < ldt * nt; e += NT) sm.Dt[e] = __ldcs(ws.J + net.o_tl + e) * con;
+  __syncthreads();
+  for (int i = tid; i < nh; i += NT) sm.hh[__ldg(net.pivmeta + i).x - 1] += 1.0;
+  for (int a = tid; a < nt; a += NT) sm.Dt[a * ldt + a] += 1.0;
+  __syncthreads();
+  long long t0b = clock64();
+  // ---- head rows, level by level, one warp per row (up-looking through a dense work row over
+  // all n columns).  The pivots k of a row and their metadata are fetched 32 at a time (one
+  // lane each) so that the sequential k-loop touches shared memory only.
+  for (int lev = 0; lev < net.nflev; ++lev) {
+    const int rb = sm.flptr[lev], re = sm.flptr[lev + 1];
+    for (int ri = rb + w; ri < re && w < NWR; ri += NWR) {
+      const int4 fm = __ldg(net.fmeta + ri);
+      const int i = fm.x, base = fm.y, nl = fm.z;
+      if (nl == 0) {   // nothing to eliminate: U(i,:) = P(i,:)
+        if (l == 0) {
+          const double d = sm.hh[base];
+          if (d == 0.0 || isnan(d)) *flag = 1;
+          sm.dinv[i] = 1.0 / d;
+        }
+        continue;
+      }
+      const int4 pm = __ldg(net.pivmeta + i);
+      const int len = pm.x + pm.y - base, u0 = pm.z, ulen = pm.w;
+      for (int q = l; q < len; q += 32) wrow[sm.hhcol[base + q]] = sm.hh[base + q];
+      for (int q = l; q < ulen; q += 32) wrow[nh + ubcol[u0 + q]] = ub[u0 + q];
+      __syncwarp();
+      for (int q0 = 0; q0 < nl; q0 += 32) {
+        const int myk = (q0 + l < nl) ? (int)sm.hhcol[base + q0 + l] : 0;
+        const int4 mm = __ldg(net.pivmeta + myk);
+        const int cnt = (nl - q0) < 32 ? (nl - q0) : 32;
+        for (int j = 0; j < cnt; ++j) {
+          const int k = __shfl_sync(0xffffffffu, myk, j);
+          const int kb = __shfl_sync(0xffffffffu, mm.x, j), klen = __shfl_sync(0xffffffffu, mm.y, j);
+          const int ku = __shfl_sync(0xffffffffu, mm.z, j), kul = __shfl_sync(0xffffffffu, mm.w, j);
+          const double lv = wrow[k] * sm.dinv[k];
+          __syncwarp();
+          if (l == 0) sm.hh[base + q0 + j] = lv;
+          for (int t = l; t < klen; t += 32) wrow[sm.hhcol[kb + t]] -= lv * sm.hh[kb + t];
+          for (int t = l; t < kul; t += 32) wrow[nh + ubcol[ku + t]] -= lv * ub[ku + t];
+          __syncwarp();
+        }
+      }
       if (l == 0) {
+        const double d = wrow[i];
         if (d == 0.0 || isnan(d)) *flag = 1;
         sm.dinv[i] = 1.0 / d;
-        ws.LU[base + nl] = d;
+        sm.hh[base + nl] = d;
       }
-      for (int q = nl + 1 + l; q < len; q += 32) ws.LU[base + q] = wrow[net.col[base + q]];
+      for (int q = nl + 1 + l; q < len; q += 32) sm.hh[base + q] = wrow[sm.hhcol[base + q]];
+      for (int q = l; q < ulen; q += 32) ub[u0 + q] = wrow[nh + ubcol[u0 + q]];
       __syncwarp();
     }
     __syncthreads();
   }
   long long t1 = clock64();
-  // ---- phase 2: tail rows against the head pivots (independent rows), Schur row into S
-  for (int a = w; a < nt; a += NW) {
-    const int i = nh + a;
-    const int base = net.row_ptr[i], nl = net.row_ptr[i + 1] - base;
-    for (int q = l; q < nl; q += 32) wrow[net.col[base + q]] = pval(base + q, false);
-    for (int b = l; b < nt; b += 32) wrow[nh + b] = pval(net.nslots + a * nt + b, a == b);
+  // ---- tail rows against the head pivots (rows are independent; longest first):
+  // multipliers L_C(a,:) -> ELL copy for the solves, Schur row -> Dt
+  for (int ai = w; ai < nt && w < NWR; ai += NWR) {
+    const int a = net.tail_order[ai];
+    const int base = net.lc_ptr[a], nl = net.lc_ptr[a + 1] - base;
+    for (int q = l; q < nl; q += 32) wrow[__ldg(net.lc_col + base + q)] = __ldcs(ws.J + net.o_lc + base + q) * con;
+    for (int b = l; b < nt; b += 32) wrow[nh + b] = sm.Dt[(size_t)b * ldt + a];
     __syncwarp();
-    for (int q = 0; q < nl; ++q) {
-      const int k = net.col[base + q];
-      const double lv = wrow[k] * sm.dinv[k];
-      if (l == 0) ws.LU[base + q] = lv;
-      const int kb = net.row_ptr[k] + net.row_nl[k] + 1, klen = net.row_ptr[k + 1] - kb;
-      for (int t = l; t < klen; t += 32) wrow[net.col[kb + t]] -= lv * ws.LU[kb + t];
-      __syncwarp();
+    for (int q0 = 0; q0 < nl; q0 += 32) {
+      const int myk = (q0 + l < nl) ? (int)__ldg(net.lc_col + base + q0 + l) : 0;
+      const int myp = (q0 + l < nl) ? __ldg(net.lc_ellpos + base + q0 + l) : 0;
+      const int4 mm = __ldg(net.pivmeta + myk);
+      const int cnt = (nl - q0) < 32 ? (nl - q0) : 32;
+      double mylv = 0.0;
+      for (int j = 0; j < cnt; ++j) {
+        const int k = __shfl_sync(0xffffffffu, myk, j);
+        const int kb = __shfl_sync(0xffffffffu, mm.x, j), klen = __shfl_sync(0xffffffffu, mm.y, j);
+        const int ku = __shfl_sync(0xffffffffu, mm.z, j), kul = __shfl_sync(0xffffffffu, mm.w, j);
+        const double lv = wrow[k] * sm.dinv[k];
+        __syncwarp();
+        if (l == j) mylv = lv;
+        for (int t = l; t < klen; t += 32) wrow[sm.hhcol[kb + t]] -= lv * sm.hh[kb + t];
+        for (int t = l; t < kul; t += 32) wrow[nh + ubcol[ku + t]] -= lv * ub[ku + t];
+        __syncwarp();
+      }
+      if (q0 + l < nl) ws.lcE[myp] = mylv;      // multipliers -> ELL copy, one coalesced-ish store per chunk
     }
-    for (int b = l; b < nt; b += 32) S[a * nt + b] = wrow[nh + b];
+    for (int b = l; b < nt; b += 32) sm.Dt[(size_t)b * ldt + a] = wrow[nh + b];
     __syncwarp();
   }
   __syncthreads();
+  // U_B in ELL order for the solves
+  for (int s = tid; s < net.n_ub; s += NT) ws.ubE[__ldg(net.ub_ellpos + s)] = ub[s];
+  __syncthreads();   // X (work rows, U_B) is reused as scratch by the dense tail below
+  if (!lay.hh_smem) __threadfence_block();
   long long t2 = clock64();
-  // ---- phase 3: dense right-looking LU of S in shared memory (no pivoting)
-  for (int k = 0; k < nt; ++k) {
-    const double d = S[k * nt + k];
-    if (d == 0.0 || isnan(d)) { if (threadIdx.x == 0) *flag = 1; }
-    const double inv = 1.0 / d;
-    if (threadIdx.x == 0) sm.dinv[nh + k] = inv;
-    __syncthreads();
-    for (int i = k + 1 + threadIdx.x; i < nt; i += NT) S[i * nt + k] *= inv;
-    __syncthreads();
-    const int m = nt - k - 1;
-    for (int e = threadIdx.x; e < m * m; e += NT) {
-      const int i = k + 1 + e / m, j = k + 1 + e % m;
-      S[i * nt + j] -= S[i * nt + k] * S[k * nt + j];
-    }
+  // ---- dense tail
+  switch (nt >> 4) {
+    case 1: tail_lu<1>(sm, sm.X, flag); break; case 2: tail_lu<2>(sm, sm.X, flag); break;
+    case 3: tail_lu<3>(sm, sm.X, flag); break; case 4: tail_lu<4>(sm, sm.X, flag); break;
+    case 5: tail_lu<5>(sm, sm.X, flag); break; case 6: tail_lu<6>(sm, sm.X, flag); break;
+    case 7: tail_lu<7>(sm, sm.X, flag); break; default: tail_lu<8>(sm, sm.X, flag); break;
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < nt * nt; e += NT) {
-    const int j = e / nt, i = e % nt;
-    ws.Dt[e] = S[i * nt + j];      // column-major copy
-  }
-  __syncthreads();
+  long long t2b = clock64();
+  tail_block_inverses(sm);
   const int res = *flag;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     long long t3 = clock64();
     ph[PH_FACT_HEAD] += t1 - t0; ph[PH_FACT_SCHUR] += t2 - t1; ph[PH_FACT_TAIL] += t3 - t2;
+    ph[PH_PBUILD] += t0b - t0; ph[PH_TAILINV] += t3 - t2b;
   }
   return res;
 }
 
-// DSOLSS: x <- P^{-1} x, x = sm.y in original species order
-// (wiped: P is pw*I, see DPRJS below)
-__device__ void solve(const DevNet& net, const Ws& ws, Smem& sm, bool wiped, double pw) {
-  const int n = net.n, nh = net.nh, nt = net.nt;
+// SpMV with an ELL coupling block: out[row] -= sum val * x[col]
+__device__ __forceinline__ void spmv_sub(const EllDev& e, const double* __restrict__ val, const double* x,
+                                         double* out, double* partial) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int b = w; b < e.nblk; b += NW) {
+    const int off = e.blk_off[b], width = e.blk_width[b];
+    double acc = 0.0;
+    for (int j0 = 0; j0 < width; j0 += 16) {
+      double vv[16]; int cc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        vv[j] = (j0 + j < width) ? __ldcs(val + off + (j0 + j) * 32 + l) : 0.0;
+        cc[j] = (j0 + j < width) ? (int)__ldg(e.col + off + (j0 + j) * 32 + l) : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (j0 + j < width) acc += vv[j] * x[cc[j]];
+    }
+    const int t = e.sub_target[b * 32 + l];
+    if (t >= 0) out[t] -= acc;
+    else if (t <= -2) partial[-2 - t] = acc;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < e.ncombine; q += NT) {
+    double s = 0.0;
+    for (int p = e.comb_ptr[q]; p < e.comb_ptr[q + 1]; ++p) s += partial[p];
+    out[e.comb_row[q]] -= s;
+  }
+  __syncthreads();
+}
+
+// DSOLSS: sm.y <- P^{-1} sm.y (original species order in, original order out)
+// (wiped: P is pw*I, see DPRJS below)
+__device__ __forceinline__ void solve(Ws ws, Smem sm, bool wiped, double pw) {
+  const DevNet& net = c_net;
+  const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, tid = threadIdx.x;
   if (wiped) {
-    for (int i = threadIdx.x; i < n; i += NT) sm.y[i] = sm.y[i] / pw;
+    for (int i = tid; i < n; i += NT) sm.y[i] = sm.y[i] / pw;
     __syncthreads();
     return;
   }
-  for (int i = threadIdx.x; i < n; i += NT) sm.xb[i] = sm.y[net.perm[i]];
+  for (int i = tid; i < n; i += NT) sm.xb[i] = sm.y[net.perm[i]];
   __syncthreads();
-  // forward, head (level 0 rows have no L entries)
-  for (int lev = 1; lev < net.nflev; ++lev) {
-    const int rb = net.flev_ptr[lev], re = net.flev_ptr[lev + 1];
-    for (int ri = rb + threadIdx.x; ri < re; ri += NT) {
-      const int i = net.flev_rows[ri];
-      const int base = net.row_ptr[i], nl = net.row_nl[i];
-      double s = sm.xb[i];
-      for (int q = 0; q < nl; ++q) s -= ws.LU[base + q] * sm.xb[net.col[base + q]];
-      sm.xb[i] = s;
+  // ---- forward, head: fat levels by the CTA, thin levels (<= 32 rows) by warp 0
+  for (int lev = 1; lev < net.nfat_f; ++lev) {
+    const int rb = sm.flptr[lev], re = sm.flptr[lev + 1];
+    for (int ri = rb + tid; ri < re; ri += NT) {
+      const int4 fm = __ldg(net.fmeta + ri);
+      double s = sm.xb[fm.x];
+      for (int q = 0; q < fm.z; ++q) s -= sm.hh[fm.y + q] * sm.xb[sm.hhcol[fm.y + q]];
+      sm.xb[fm.x] = s;
     }
     __syncthreads();
   }
-  // forward, tail rows against head unknowns (independent rows; warp per row)
-  for (int a = w; a < nt; a += NW) {
-    const int i = nh + a;
-    const int base = net.row_ptr[i], nl = net.row_ptr[i + 1] - base;
-    double s = 0.0;
-    for (int q = l; q < nl; q += 32) s += ws.LU[base + q] * sm.xb[net.col[base + q]];
-    s = warp_sum(s);
-    if (l == 0) sm.xb[i] -= s;
-  }
-  __syncthreads();
-  // dense tail: unit-lower forward then upper backward, one warp, column oriented
   if (w == 0) {
-    double* xt = sm.xb + nh;
-    for (int j = 0; j < nt; ++j) {
-      const double xj = xt[j];
-      const double* cj = ws.Dt + (size_t)j * nt;
-      for (int i = j + 1 + l; i < nt; i += 32) xt[i] -= cj[i] * xj;
-      __syncwarp();
-    }
-    for (int j = nt - 1; j >= 0; --j) {
-      const double xj = xt[j] * sm.dinv[nh + j];
-      __syncwarp();
-      if (l == 0) xt[j] = xj;
-      const double* cj = ws.Dt + (size_t)j * nt;
-      for (int i = l; i < j; i += 32) xt[i] -= cj[i] * xj;
+    const int off = net.flev_nfat_rows;
+    for (int lev = (net.nfat_f > 1 ? net.nfat_f : 1); lev < net.nflev; ++lev) {
+      const int rb = sm.flptr[lev], re = sm.flptr[lev + 1];
+      if (rb + l < re) {
+        const int4 fm = sm.fthin[rb + l - off];
+        double s = sm.xb[fm.x];
+        for (int q = 0; q < fm.z; ++q) s -= sm.hh[fm.y + q] * sm.xb[sm.hhcol[fm.y + q]];
+        sm.xb[fm.x] = s;
+      }
       __syncwarp();
     }
   }
   __syncthreads();
-  // backward, head rows
-  for (int lev = 0; lev < net.nsu; ++lev) {
-    const int rb = net.su_ptr[lev], re = net.su_ptr[lev + 1];
-    for (int ri = rb + threadIdx.x; ri < re; ri += NT) {
-      const int i = net.su_rows[ri];
-      const int ub = net.row_ptr[i] + net.row_nl[i] + 1, ue = net.row_ptr[i + 1];
-      double s = sm.xb[i];
-      for (int q = ub; q < ue; ++q) s -= ws.LU[q] * sm.xb[net.col[q]];
-      sm.xb[i] = s * sm.dinv[i];
+  // ---- tail right-hand side: x_T -= L_C x_H
+  spmv_sub(net.lcE, ws.lcE, sm.xb, sm.xb + nh, sm.X);
+  // ---- dense tail by one warp: x in registers, 32-blocks, inverted diagonal blocks
+  if (w == 0) {
+    const int nb = (nt + 31) >> 5;
+    double x[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) x[m] = (m < nb && 32 * m + l < nt) ? sm.xb[nh + 32 * m + l] : 0.0;
+    // forward: unit lower
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (m < nb) {
+        const int r = 32 * m + l;
+        const bool valid = r < nt;
+        double a0 = x[m], a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const double x0 = __shfl_sync(0xffffffffu, x[m], j), x1 = __shfl_sync(0xffffffffu, x[m], j + 1);
+          if (valid && j < l && 32 * m + j < nt) a0 += sm.Dt[(size_t)(32 * m + j) * ldt + r] * x0;
+          if (valid && j + 1 < l && 32 * m + j + 1 < nt) a1 += sm.Dt[(size_t)(32 * m + j + 1) * ldt + r] * x1;
+        }
+        x[m] = a0 + a1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const double xj = __shfl_sync(0xffffffffu, x[m], j);
+          if (32 * m + j < nt) {
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm)
+              if (mm > m && mm < nb && 32 * mm + l < nt) x[mm] -= sm.Dt[(size_t)(32 * m + j) * ldt + 32 * mm + l] * xj;
+          }
+        }
+      }
+    }
+    // backward: upper, diagonal blocks hold U^{-1}
+#pragma unroll
+    for (int m = 3; m >= 0; --m) {
+      if (m < nb) {
+        const int r = 32 * m + l;
+        const bool valid = r < nt;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const double x0 = __shfl_sync(0xffffffffu, x[m], j), x1 = __shfl_sync(0xffffffffu, x[m], j + 1);
+          if (valid && j >= l && 32 * m + j < nt) a0 += sm.Dt[(size_t)(32 * m + j) * ldt + r] * x0;
+          if (valid && j + 1 >= l && 32 * m + j + 1 < nt) a1 += sm.Dt[(size_t)(32 * m + j + 1) * ldt + r] * x1;
+        }
+        x[m] = a0 + a1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const double xj = __shfl_sync(0xffffffffu, x[m], j);
+          if (32 * m + j < nt) {
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm)
+              if (mm < m && 32 * mm + l < nt) x[mm] -= sm.Dt[(size_t)(32 * m + j) * ldt + 32 * mm + l] * xj;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) if (m < nb && 32 * m + l < nt) sm.xb[nh + 32 * m + l] = x[m];
+  }
+  __syncthreads();
+  // ---- head right-hand side: x_H -= U_B x_T
+  spmv_sub(net.ubE, ws.ubE, sm.xb + nh, sm.xb, sm.X);
+  // ---- backward, head
+  for (int lev = 0; lev < net.nfat_b; ++lev) {
+    const int rb = sm.suptr[lev], re = sm.suptr[lev + 1];
+    for (int ri = rb + tid; ri < re; ri += NT) {
+      const int4 bm = __ldg(net.bmeta + ri);
+      double s = sm.xb[bm.x];
+      for (int q = 0; q < bm.z; ++q) s -= sm.hh[bm.y + q] * sm.xb[sm.hhcol[bm.y + q]];
+      sm.xb[bm.x] = s * sm.dinv[bm.x];
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < n; i += NT) sm.y[net.perm[i]] = sm.xb[i];
+  if (w == 0) {
+    const int off = net.su_nfat_rows;
+    for (int lev = net.nfat_b; lev < net.nsu; ++lev) {
+      const int rb = sm.suptr[lev], re = sm.suptr[lev + 1];
+      if (rb + l < re) {
+        const int4 bm = sm.bthin[rb + l - off];
+        double s = sm.xb[bm.x];
+        for (int q = 0; q < bm.z; ++q) s -= sm.hh[bm.y + q] * sm.xb[sm.hhcol[bm.y + q]];
+        sm.xb[bm.x] = s * sm.dinv[bm.x];
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) sm.y[net.perm[i]] = sm.xb[i];
   __syncthreads();
 }
 
@@ -339,43 +688,68 @@ enum { L100, L150, L160, L170, L175, L200, L220, L250, L270, L410, L430, L450, L
        L610, L620, L630, L640, L660, L670, L680, L690, L700, L720 };
 
 struct Lsodes {      // COMMON /DLS001/ + /DLSS01/ (uniform across the CTA, held in registers)
-  double CONIT, CRATE, EL[7], HOLD, RMAX, CCMAX, EL0, H, HMIN, HMXI, HU, RC, TN, UROUND;
-  double CON0, CONMIN, CCMXJ, PSMALL, RBIG, TCRIT;
-  int MXSTEP, NSLAST, IALTH, IPUP, LMAX, NSLP, ICF, IERPJ, IERSL, JCUR, JSTART, KFLAG, L;
-  int MAXORD, MAXCOR, MSBP, MXNCF, NQ, NST, NFE, NJE, NQU, MSBJ, NSLJ, NLU, IMXER, IPLOST, INIT;
+  double CONIT, CRATE, EL1, EL2, EL3, EL4, EL5, EL6, HOLD, RMAX, EL0, H, HMXI, HU, RC, TN;
+  double CON0, CONMIN, TCRIT;
+  int MXSTEP, NSLAST, IALTH, IPUP, NSLP, ICF, IERPJ, IERSL, JCUR, JSTART, KFLAG, L;
+  int NQ, NST, NFE, NJE, NQU, NSLJ, NLU, IMXER, IPLOST, INIT;
+  // constants of the method as the reference's driver sets them (src/opkdmain.f:3305-3322)
+  static constexpr double UROUND = 2.220446049250313e-16, CCMAX = 0.3, CCMXJ = 0.2, HMIN = 0.0,
+                          PSMALL = 1000.0 * 2.220446049250313e-16, RBIG = 0.01 / (1000.0 * 2.220446049250313e-16);
+  static constexpr int MAXORD = 5, LMAX = 6, MAXCOR = 3, MSBP = 20, MXNCF = 10, MSBJ = 50;
   int wiped;         // saved P zeroed by ISTATE=1/3 preprocessing and not yet rebuilt from a fresh J
   double pw;         // while wiped: P = pw * I
   bool IHIT;
   long long n_solve, n_cfail, n_efail;
 };
 
+template <int EPT, bool ALLSMEM>
 __global__ void __launch_bounds__(NT, 1)
-integrate_kernel(const DevNet net, const BatchArgs args) {
+integrate_kernel(const BatchArgs args) {
+  const DevNet& net = c_net;
   extern __shared__ __align__(16) double smem_raw[];
   __shared__ int s_cell, s_flag;
+  __shared__ unsigned long long s_ph[PH_COUNT];   // per-phase cycle counters (thread 0 only)
   const int n = net.n, NEQ = net.NEQ, R = net.R;
   const int tid = threadIdx.x;
-  Smem sm;
-  {
-    double* p = smem_raw;
-    sm.yh = p; p += 6 * n; sm.y = p; p += n; sm.savf = p; p += n; sm.acor = p; p += n;
-    sm.ewt = p; p += n; sm.xb = p; p += n; sm.dinv = p; p += n; sm.par = p; p += 32;
-    sm.red = p; p += 2 * NW; sm.X = p;
-  }
-  double* kx = sm.X;                 // rates [R]
-  double* fx = sm.X + R;             // flux [R] / dflux [2R]
+  const Layout lay = make_layout(net);
   Ws ws;
   {
     double* p = args.ws + (size_t)blockIdx.x * args.ws_stride;
-    ws.J = p; p += net.nJ; ws.LU = p; p += net.nslots; ws.Dt = p; p += net.nt * net.nt;
-    ws.ksave = p; p += R; ws.rtol = p; p += NEQ; ws.atol = p; p += NEQ;
+    ws.J = p; p += net.nstore; ws.ubE = p; p += net.ubE.nval; ws.lcE = p; p += net.lcE.nval;
+    ws.ksave = p; p += R; ws.hhG = p; p += net.n_hh; ws.ubG = p; p += net.n_ub;
   }
-  unsigned long long ph[PH_COUNT];
-  for (int k = 0; k < PH_COUNT; ++k) ph[k] = 0;
+  Smem sm;
+  {
+    double* p = smem_raw;
+    sm.y = p; p += n; sm.savf = p; p += n; sm.xb = sm.savf; sm.dinv = p; p += net.nh;
+    sm.par = p; p += 32; sm.red = p; p += 2 * NW; sm.Dt = p; p += (size_t)net.ldt * net.nt;
+    if (ALLSMEM || lay.hh_smem) { sm.hh = p; p += net.n_hh; } else sm.hh = ws.hhG;
+    // index tables (staged below, once per CTA)
+    const int nthin_f = net.nh - net.flev_nfat_rows, nthin_b = net.nh - net.su_nfat_rows;
+    if ((size_t)p & 15) p += 1;   // int4 tables need 16-byte alignment
+    int4* ft = (int4*)p; p += 2 * nthin_f; int4* bt = (int4*)p; p += 2 * nthin_b;
+    int* fl = (int*)p; int* su = fl + (net.nflev + 1);
+    p += ((size_t)(net.nflev + net.nsu + 2) * 4 + 7) / 8;
+    uint16_t* hc = (uint16_t*)p; p += ((size_t)net.n_hh * 2 + 7) / 8;
+    for (int q = tid; q < nthin_f; q += NT) ft[q] = net.fmeta[net.flev_nfat_rows + q];
+    for (int q = tid; q < nthin_b; q += NT) bt[q] = net.bmeta[net.su_nfat_rows + q];
+    for (int q = tid; q <= net.nflev; q += NT) fl[q] = net.flev_ptr[q];
+    for (int q = tid; q <= net.nsu; q += NT) su[q] = net.su_ptr[q];
+    for (int q = tid; q < net.n_hh; q += NT) hc[q] = net.hh_col[q];
+    sm.fthin = ft; sm.bthin = bt; sm.flptr = fl; sm.suptr = su; sm.hhcol = hc;
+    sm.X = p;
+  }
+  double* fx = sm.X;                 // flux / dflux [R]
+  double* px = sm.X + R;             // gather partials
+  const double* ks = ws.ksave;
+  unsigned long long* const ph = s_ph;
+  if (tid < PH_COUNT) s_ph[tid] = 0;
+  __syncthreads();
   const long long tk0 = clock64();
   const int ncell = args.ncell;
-#define YH(i, j) sm.yh[((j) - 1) * n + (i)]
-#define VEC(i) for (int i = tid; i < n; i += NT)
+  // element e of this thread is species i = tid + e*NT
+  double yh[EPT][6], acor[EPT], ewt[EPT], rt[EPT], at[EPT];
+#define FORE _Pragma("unroll") for (int e = 0, i = tid; e < EPT; ++e, i += NT) if (i < n)
   for (;;) {
     __syncthreads();
     if (tid == 0) s_cell = atomicAdd(args.queue, 1);
@@ -385,46 +759,48 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
     long long tc = clock64();
     // ---- load the cell
     if (tid < RACG_NPAR) sm.par[tid] = args.cellpar[(size_t)tid * ncell + cell];
-    VEC(i) sm.y[i] = args.y0[(size_t)i * ncell + cell];
+    FORE sm.y[i] = args.y0[(size_t)i * ncell + cell];
     const double Tslot = args.y0[(size_t)(NEQ - 1) * ncell + cell];
     __syncthreads();
     const double DS = sm.par[RACG_P_ratioDust2HnucNum] * sm.par[RACG_P_SitesPerGrain];
     // tolerances: given, or chem_set_solver_flags_alt(j) (src/chemistry.f90:205-268)
+    double rtT, atT;
     if (args.rtol) {
-      for (int i = tid; i < NEQ; i += NT) {
-        ws.rtol[i] = args.rtol[(size_t)i * ncell + cell];
-        ws.atol[i] = args.atol[(size_t)i * ncell + cell];
-      }
+      FORE { rt[e] = args.rtol[(size_t)i * ncell + cell]; at[e] = args.atol[(size_t)i * ncell + cell]; }
+      rtT = args.rtol[(size_t)(NEQ - 1) * ncell + cell]; atT = args.atol[(size_t)(NEQ - 1) * ncell + cell];
     } else {
       const int j = args.sp.tol_policy_j;
       const double RT = args.sp.RTOL, AT = args.sp.ATOL, D = sm.par[RACG_P_ratioDust2HnucNum];
-      double r, a, rT, aT;
-      if (j == 1) { r = RT; a = AT; rT = 1e-3; aT = 1e-1; }
-      else if (j == 2) { r = fmin(RT * 1e1, 1e-4); a = fmin(AT * 1e5, 1e-25); rT = 1e-2; aT = 1e-1; }
-      else if (j == 3) { r = fmin(RT * 1e2, 1e-4); a = fmin(AT * 1e10, 1e-20); rT = 1e-3; aT = 1.0; }
-      else if (j == 4) { r = fmin(RT * 1e2, 1e-4); a = fmin(AT * 1e10, 1e-18); rT = 1e-3; aT = 1.0; }
-      else { r = fmin(RT * pow(2.0, (double)j), 1e-3); a = fmin(AT * pow(1e2, (double)j), 1e-15); rT = 1e-2; aT = 1.0; }
-      for (int i = tid; i < NEQ; i += NT) { ws.rtol[i] = (i == NEQ - 1) ? rT : r; ws.atol[i] = (i == NEQ - 1) ? aT : a; }
+      double r, a;
+      if (j == 1) { r = RT; a = AT; rtT = 1e-3; atT = 1e-1; }
+      else if (j == 2) { r = fmin(RT * 1e1, 1e-4); a = fmin(AT * 1e5, 1e-25); rtT = 1e-2; atT = 1e-1; }
+      else if (j == 3) { r = fmin(RT * 1e2, 1e-4); a = fmin(AT * 1e10, 1e-20); rtT = 1e-3; atT = 1.0; }
+      else if (j == 4) { r = fmin(RT * 1e2, 1e-4); a = fmin(AT * 1e10, 1e-18); rtT = 1e-3; atT = 1.0; }
+      else { r = fmin(RT * pow(2.0, (double)j), 1e-3); a = fmin(AT * pow(1e2, (double)j), 1e-15); rtT = 1e-2; atT = 1.0; }
+      // stage through shared memory (xb is free here) to apply the per-species overrides in order
+      double* trt = sm.X; double* tat = sm.X + n;
+      FORE { trt[i] = r; tat[i] = a; }
       __syncthreads();
-      if (tid < 10 && net.hc_idx[tid] >= 0) { ws.rtol[net.hc_idx[tid]] = fmax(RT, 1e-4); ws.atol[net.hc_idx[tid]] = fmax(AT, 1e-30); }
+      if (tid < 10 && net.hc_idx[tid] >= 0) { trt[net.hc_idx[tid]] = fmax(RT, 1e-4); tat[net.hc_idx[tid]] = fmax(AT, 1e-30); }
       __syncthreads();
       if (tid == 0 && net.iGrain0 >= 0) {
         const int g3[3] = {net.iGrain0, net.iGrainM, net.iGrainP};
-        for (int q = 0; q < 3; ++q) if (g3[q] >= 0) { ws.rtol[g3[q]] = 1e-4; ws.atol[g3[q]] = fmax(D * 1e-6, 1e-30); }
+        for (int q = 0; q < 3; ++q) if (g3[q] >= 0) { trt[g3[q]] = 1e-4; tat[g3[q]] = fmax(D * 1e-6, 1e-30); }
       }
       __syncthreads();
-      for (int q = tid; q < net.ngrain; q += NT) { ws.rtol[net.grain_idx[q]] = fmax(RT, 1e-3); ws.atol[net.grain_idx[q]] = fmax(AT, D * 1e-8); }
+      for (int q = tid; q < net.ngrain; q += NT) { trt[net.grain_idx[q]] = fmax(RT, 1e-3); tat[net.grain_idx[q]] = fmax(AT, D * 1e-8); }
+      __syncthreads();
+      FORE { rt[e] = trt[i]; at[e] = tat[i]; }
+      __syncthreads();
     }
-    __syncthreads();
-    // ---- K1: rate coefficients of this cell
+    // ---- K1: rate coefficients of this cell -> workspace (L2)
     {
       CellCommon cc;
       cell_common(net.cfg, [&](int k) { return sm.par[k]; }, cc);
-      for (int r = tid; r < R; r += NT) kx[r] = rate_coeff(net, cc, r);
+      for (int r = tid; r < R; r += NT) ws.ksave[r] = rate_coeff(net, cc, r);
       __syncthreads();
-      for (int d = tid; d < net.ndup; d += NT) resolve_dupli(net, cc.Tgas, d, [&](int z) { kx[z] = 0.0; });
+      for (int d = tid; d < net.ndup; d += NT) resolve_dupli(net, cc.Tgas, d, [&](int z) { ws.ksave[z] = 0.0; });
       __syncthreads();
-      for (int r = tid; r < R; r += NT) ws.ksave[r] = kx[r];
     }
     if (tid == 0) { long long t = clock64(); ph[PH_RATES] += t - tc; }
 
@@ -445,9 +821,15 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
       if (args.touts && tid == 0) args.touts[(size_t)(irec - 1) * ncell + cell] = t;
       if (args.record) {
         double* rp = args.record + (size_t)(irec - 1) * NEQ * ncell + cell;
-        VEC(i) rp[(size_t)i * ncell] = sm.y[i];
+        for (int i = tid; i < n; i += NT) rp[(size_t)i * ncell] = sm.y[i];
         if (tid == 0) rp[(size_t)(NEQ - 1) * ncell] = Tslot;
       }
+    };
+    // DVNORM of a register vector against EWT (N = NEQ as in the reference)
+    auto wrms_reg = [&](auto getv) -> double {
+      double sq = 0.0;
+      FORE { const double a = getv(e, i) * ewt[e]; sq += a * a; }
+      return sqrt(block_sum(sq, sm.red) / (double)NEQ);
     };
     record_out(1);
     int irec;
@@ -458,13 +840,13 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
       {
         const double TOUT = tout;
         int dl;   // driver label
-        enum { D_BLOCKC, D200, D245, D250, D270, D_STEP, D_AFTER, D345, D400, D420, D560, D580, D_RET };
+        enum { D_BLOCKC, D200, D245, D250, D270, D_STEP, D_AFTER, D_INTERP, D345, D400, D420, D560, D580, D_RET };
         if (ISTATE == 1 && TOUT == t) { dl = D_RET; }
         else if (ISTATE == 2) dl = D200;
         else {
           // Block B
-          s.MAXORD = 5; s.MXSTEP = args.sp.mxstep_per_interval; if (s.MXSTEP == 0) s.MXSTEP = 500;
-          s.HMXI = (t_max > 0.0) ? 1.0 / t_max : 0.0; s.HMIN = 0.0;
+          s.MXSTEP = args.sp.mxstep_per_interval; if (s.MXSTEP == 0) s.MXSTEP = 500;
+          s.HMXI = (t_max > 0.0) ? 1.0 / t_max : 0.0;
           s.wiped = 1; s.pw = 0.0;   // DPREP zeroes the saved P (src/opkda1.f:1493-1494)
           if (ISTATE == 3) { s.JSTART = -1; dl = D200; }
           else dl = D_BLOCKC;
@@ -475,44 +857,32 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
           switch (dl) {
             case D_BLOCKC: {
               s.TN = t; s.NST = 0; s.H = 1.0;
-              VEC(i) YH(i, 1) = sm.y[i];
-              __syncthreads();
-              { long long ta = clock64(); eval_f(net, kx, fx, fx + R, sm.y, &YH(0, 2), DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+              FORE { yh[e][0] = sm.y[i]; yh[e][2] = 0.0; yh[e][3] = 0.0; yh[e][4] = 0.0; yh[e][5] = 0.0; }
+              { long long ta = clock64(); eval_f(ks, fx, px, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+              FORE yh[e][1] = sm.savf[i];
               s.NFE = 1;
               bool bad = false;
-              VEC(i) { const double e = ws.rtol[i] * fabs(YH(i, 1)) + ws.atol[i]; if (e <= 0.0) bad = true; sm.ewt[i] = 1.0 / e; }
+              FORE { const double ew = rt[e] * fabs(yh[e][0]) + at[e]; if (ew <= 0.0) bad = true; ewt[e] = 1.0 / ew; }
               if (__syncthreads_or(bad)) { ISTATE = -3; dl = D_RET; break; }
               s.TCRIT = t_max;
               if ((s.TCRIT - TOUT) * (TOUT - t) < 0.0) { ISTATE = -3; dl = D_RET; break; }
-              s.UROUND = 2.220446049250313e-16;
-              s.JSTART = 0; s.MSBJ = 50; s.NSLJ = 0; s.CCMXJ = 0.2; s.PSMALL = 1000.0 * s.UROUND;
-              s.RBIG = 0.01 / s.PSMALL; s.NJE = 0; s.NLU = 0; s.NSLAST = 0; s.HU = 0.0; s.NQU = 0;
-              s.CCMAX = 0.3; s.MAXCOR = 3; s.MSBP = 20; s.MXNCF = 10; s.IPLOST = 0; s.CON0 = 0.0; s.CONMIN = 0.0;
+              s.JSTART = 0; s.NSLJ = 0; s.NJE = 0; s.NLU = 0; s.NSLAST = 0; s.HU = 0.0; s.NQU = 0;
+              s.IPLOST = 0; s.CON0 = 0.0; s.CONMIN = 0.0;
               const double TDIST = fabs(TOUT - t), W0 = fmax(fabs(t), fabs(TOUT));
               if (TDIST < 2.0 * s.UROUND * W0) { ISTATE = -3; dl = D_RET; break; }
-              double TOL = 0.0;
-              for (int i = tid; i < NEQ; i += NT) TOL = fmax(TOL, ws.rtol[i]);
-              {  // block max
-                for (int o = 16; o > 0; o >>= 1) TOL = fmax(TOL, __shfl_xor_sync(0xffffffffu, TOL, o));
-                __syncthreads();
-                if ((tid & 31) == 0) sm.red[tid >> 5] = TOL;
-                __syncthreads();
-                TOL = sm.red[0];
-                for (int k = 1; k < NW; ++k) TOL = fmax(TOL, sm.red[k]);
-              }
+              double TOL = rtT;
+              FORE TOL = fmax(TOL, rt[e]);
+              TOL = block_max(TOL, sm.red);
               if (TOL <= 0.0) {
                 double tl = 0.0;
-                VEC(i) { const double ay = fabs(sm.y[i]); if (ay != 0.0) tl = fmax(tl, ws.atol[i] / ay); }
-                for (int o = 16; o > 0; o >>= 1) tl = fmax(tl, __shfl_xor_sync(0xffffffffu, tl, o));
-                __syncthreads();
-                if ((tid & 31) == 0) sm.red[tid >> 5] = tl;
-                __syncthreads();
-                for (int k = 0; k < NW; ++k) TOL = fmax(TOL, sm.red[k]);
-                if (Tslot != 0.0) TOL = fmax(TOL, ws.atol[NEQ - 1] / fabs(Tslot));
+                FORE { const double ay = fabs(yh[e][0]); if (ay != 0.0) tl = fmax(tl, at[e] / ay); }
+                tl = block_max(tl, sm.red);
+                TOL = fmax(TOL, tl);
+                if (Tslot != 0.0) TOL = fmax(TOL, atT / fabs(Tslot));
               }
               TOL = fmax(TOL, 100.0 * s.UROUND);
               TOL = fmin(TOL, 0.001);
-              double SUM = wrms(&YH(0, 2), sm.ewt, n, NEQ, sm.red);
+              double SUM = wrms_reg([&](int e, int) { return yh[e][1]; });
               SUM = 1.0 / (TOL * W0 * W0) + TOL * SUM * SUM;
               H0 = 1.0 / sqrt(SUM);
               H0 = fmin(H0, TDIST);
@@ -520,8 +890,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
               const double RH = fabs(H0) * s.HMXI;
               if (RH > 1.0) H0 = H0 / RH;
               s.H = H0;
-              VEC(i) YH(i, 2) = H0 * YH(i, 2);
-              __syncthreads();
+              FORE yh[e][1] = H0 * yh[e][1];
               dl = D270;
               break;
             }
@@ -531,7 +900,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
               if ((s.TN - s.TCRIT) * s.H > 0.0) { ISTATE = -3; dl = D_RET; break; }
               if ((s.TCRIT - TOUT) * s.H < 0.0) { ISTATE = -3; dl = D_RET; break; }
               if ((s.TN - TOUT) * s.H < 0.0) { dl = D245; break; }
-              dl = D_AFTER + 100;   // interpolate (handled below)
+              dl = D_INTERP;
               break;
             }
             case D245: {
@@ -548,16 +917,16 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
             case D250: {
               if ((s.NST - s.NSLAST) >= s.MXSTEP) { ISTATE = -1; dl = D580; break; }
               bool bad = false;
-              VEC(i) { const double e = ws.rtol[i] * fabs(YH(i, 1)) + ws.atol[i]; if (e <= 0.0) bad = true; sm.ewt[i] = 1.0 / e; }
+              FORE { const double ew = rt[e] * fabs(yh[e][0]) + at[e]; if (ew <= 0.0) bad = true; ewt[e] = 1.0 / ew; }
               if (__syncthreads_or(bad)) { ISTATE = -6; dl = D580; break; }
               dl = D270;
               break;
             }
             case D270: {
               double sq = 0.0;
-              VEC(i) { const double a = YH(i, 1) * sm.ewt[i]; sq += a * a; }
+              FORE { const double a = yh[e][0] * ewt[e]; sq += a * a; }
               sq = block_sum(sq, sm.red);
-              { const double eT = ws.rtol[NEQ - 1] * fabs(Tslot) + ws.atol[NEQ - 1]; const double a = Tslot / eT; sq += a * a; }
+              { const double eT = rtT * fabs(Tslot) + atT; const double a = Tslot / eT; sq += a * a; }
               double TOLSF = s.UROUND * sqrt(sq / (double)NEQ);
               if (TOLSF > 1.0) {
                 if (s.NST == 0) { ISTATE = -3; dl = D_RET; break; }
@@ -577,7 +946,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
               else if (s.JSTART == -1) pc = L100;
               else if (s.JSTART == -2) pc = L160;
               else {
-                s.LMAX = s.MAXORD + 1; s.NQ = 1; s.L = 2; s.IALTH = 2; s.RMAX = 10000.0; s.RC = 0.0;
+                s.NQ = 1; s.L = 2; s.IALTH = 2; s.RMAX = 10000.0; s.RC = 0.0;
                 s.EL0 = 1.0; s.CRATE = 0.7; s.HOLD = s.H; s.NSLP = 0; s.IPUP = 1; IRET = 3;
                 pc = L150;
               }
@@ -585,14 +954,15 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                 if (pc == L720) break;
                 switch (pc) {
                   case L100:
-                    s.IPUP = 1; s.LMAX = s.MAXORD + 1;
+                    s.IPUP = 1;
                     if (s.IALTH == 1) s.IALTH = 2;
                     pc = L160;
                     break;
                   case L150:
-                    for (int i = 1; i <= s.L; ++i) s.EL[i] = net.el[s.NQ][i];
-                    s.RC = s.RC * s.EL[1] / s.EL0;
-                    s.EL0 = s.EL[1];
+                    s.EL1 = net.el[s.NQ][1]; s.EL2 = net.el[s.NQ][2]; s.EL3 = net.el[s.NQ][3];
+                    s.EL4 = net.el[s.NQ][4]; s.EL5 = net.el[s.NQ][5]; s.EL6 = net.el[s.NQ][6];
+                    s.RC = s.RC * s.EL1 / s.EL0;
+                    s.EL0 = s.EL1;
                     s.CONIT = 0.5 / (s.NQ + 2);
                     pc = (IRET == 1) ? L160 : (IRET == 2) ? L170 : L200;
                     break;
@@ -607,8 +977,8 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                     RH = fmin(RH, s.RMAX);
                     RH = RH / fmax(1.0, fabs(s.H) * s.HMXI * RH);
                     double Rj = 1.0;
-                    for (int j = 2; j <= s.L; ++j) { Rj = Rj * RH; VEC(i) YH(i, j) = YH(i, j) * Rj; }
-                    __syncthreads();
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) { if (j < s.L) { Rj = Rj * RH; FORE yh[e][j] = yh[e][j] * Rj; } }
                     s.H = s.H * RH; s.RC = s.RC * RH; s.IALTH = s.L;
                     pc = (IREDO == 0) ? L690 : L200;
                     break;
@@ -617,22 +987,23 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                     if (fabs(s.RC - 1.0) > s.CCMAX) s.IPUP = 1;
                     if (s.NST >= s.NSLP + s.MSBP) s.IPUP = 1;
                     s.TN = s.TN + s.H;
-                    // Pascal-triangle prediction: per element, same operation order as the
-                    // flat YH1 sweep of src/opkda1.f:868-874
-                    VEC(i) {
-                      for (int JB = 1; JB <= s.NQ; ++JB)
-                        for (int j = s.NQ + 1 - JB; j <= s.NQ; ++j) YH(i, j) = YH(i, j) + YH(i, j + 1);
+                    // Pascal-triangle prediction, same per-element operation order as the flat
+                    // YH1 sweep of src/opkda1.f:868-874
+#pragma unroll
+                    for (int JB = 1; JB <= 5; ++JB) {
+                      if (JB <= s.NQ) {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) { if (j >= s.NQ - JB && j < s.NQ) FORE yh[e][j] = yh[e][j] + yh[e][j + 1]; }
+                      }
                     }
-                    __syncthreads();
                     pc = L220;
                     break;
                   }
                   case L220: {
                     M = 0;
-                    VEC(i) sm.y[i] = YH(i, 1);
-                    __syncthreads();
+                    FORE sm.y[i] = yh[e][0];
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); eval_f(net, kx, fx, fx + R, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); eval_f(ks, fx, px, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     if (s.IPUP <= 0) { pc = L250; break; }
@@ -665,7 +1036,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                         s.JCUR = 1; s.NJE = s.NJE + 1; s.NSLJ = s.NST; s.IPLOST = 0; s.CONMIN = fabs(CON);
                         if (tid == 0) ph[PH_VEC] += clock64() - tv;
                         long long ta = clock64();
-                        eval_jac(net, kx, fx, fx + 2 * R, sm.y, ws.J, DS);
+                        eval_jac(ks, fx, px, sm.y, ws.J, DS);
                         if (tid == 0) ph[PH_JAC] += clock64() - ta;
                         tv = clock64();
                         s.wiped = 0;
@@ -676,10 +1047,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                         flag = (s.pw == 0.0 || isnan(s.pw)) ? 1 : 0;
                       } else {
                         if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                        flag = factor(net, ws, sm, CON, &s_flag, ph);
-                        // reload the rates that the factorisation scratch overwrote
-                        for (int r = tid; r < R; r += NT) kx[r] = ws.ksave[r];
-                        __syncthreads();
+                        flag = factor<ALLSMEM>(ws, sm, lay, CON, &s_flag, ph);
                         tv = clock64();
                       }
                       s.CON0 = CON;
@@ -691,17 +1059,17 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                     break;
                   }
                   case L250:
-                    VEC(i) sm.acor[i] = 0.0;
+                    FORE acor[e] = 0.0;
                   case L270: {
-                    VEC(i) sm.y[i] = s.H * sm.savf[i] - (YH(i, 2) + sm.acor[i]);
+                    __syncthreads();
+                    FORE sm.y[i] = s.H * sm.savf[i] - (yh[e][1] + acor[e]);
                     __syncthreads();
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); solve(net, ws, sm, s.wiped != 0, s.pw); if (tid == 0) ph[PH_SOLVE] += clock64() - ta; }
+                    { long long ta = clock64(); solve(ws, sm, s.wiped != 0, s.pw); if (tid == 0) ph[PH_SOLVE] += clock64() - ta; }
                     tv = clock64();
                     s.n_solve++;
-                    DEL = wrms(sm.y, sm.ewt, n, NEQ, sm.red);
-                    VEC(i) { sm.acor[i] = sm.acor[i] + sm.y[i]; sm.y[i] = YH(i, 1) + s.EL[1] * sm.acor[i]; }
-                    __syncthreads();
+                    DEL = wrms_reg([&](int, int i) { return sm.y[i]; });
+                    FORE { acor[e] = acor[e] + sm.y[i]; sm.y[i] = yh[e][0] + s.EL1 * acor[e]; }
                     if (M != 0) s.CRATE = fmax(0.2 * s.CRATE, DEL / DELP);
                     DCON = DEL * fmin(1.0, 1.5 * s.CRATE) / (net.tesco[s.NQ][2] * s.CONIT);
                     if (DCON <= 1.0) { pc = L450; break; }
@@ -710,7 +1078,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                     if (M >= 2 && DEL > 2.0 * DELP) { pc = L410; break; }
                     DELP = DEL;
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); eval_f(net, kx, fx, fx + R, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); __syncthreads(); eval_f(ks, fx, px, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     pc = L270;
@@ -723,11 +1091,13 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                     break;
                   case L430: {
                     s.ICF = 2; NCF = NCF + 1; s.n_cfail++; s.RMAX = 2.0; s.TN = TOLD;
-                    VEC(i) {
-                      for (int JB = 1; JB <= s.NQ; ++JB)
-                        for (int j = s.NQ + 1 - JB; j <= s.NQ; ++j) YH(i, j) = YH(i, j) - YH(i, j + 1);
+#pragma unroll
+                    for (int JB = 1; JB <= 5; ++JB) {
+                      if (JB <= s.NQ) {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) { if (j >= s.NQ - JB && j < s.NQ) FORE yh[e][j] = yh[e][j] - yh[e][j + 1]; }
+                      }
                     }
-                    __syncthreads();
                     if (s.IERPJ < 0 || s.IERSL < 0) { pc = L680; break; }
                     if (fabs(s.H) <= s.HMIN * 1.00001) { pc = L670; break; }
                     if (NCF == s.MXNCF) { pc = L670; break; }
@@ -738,27 +1108,32 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                   case L450: {
                     s.JCUR = 0;
                     if (M == 0) DSM = DEL / net.tesco[s.NQ][2];
-                    if (M > 0) DSM = wrms(sm.acor, sm.ewt, n, NEQ, sm.red) / net.tesco[s.NQ][2];
+                    if (M > 0) DSM = wrms_reg([&](int e, int) { return acor[e]; }) / net.tesco[s.NQ][2];
                     if (DSM > 1.0) { pc = L500; break; }
                     s.KFLAG = 0; IREDO = 0; s.NST = s.NST + 1; s.HU = s.H; s.NQU = s.NQ;
-                    VEC(i) { for (int j = 1; j <= s.L; ++j) YH(i, j) = YH(i, j) + s.EL[j] * sm.acor[i]; }
-                    __syncthreads();
+#pragma unroll
+                    {
+                      const double elv[6] = {s.EL1, s.EL2, s.EL3, s.EL4, s.EL5, s.EL6};
+#pragma unroll
+                      for (int j = 0; j < 6; ++j) { if (j < s.L) FORE yh[e][j] = yh[e][j] + elv[j] * acor[e]; }
+                    }
                     s.IALTH = s.IALTH - 1;
                     if (s.IALTH == 0) { pc = L520; break; }
                     if (s.IALTH > 1) { pc = L700; break; }
                     if (s.L == s.LMAX) { pc = L700; break; }
-                    VEC(i) YH(i, s.LMAX) = sm.acor[i];
-                    __syncthreads();
+                    FORE yh[e][5] = acor[e];     // YH(:,LMAX), LMAX = 6
                     pc = L700;
                     break;
                   }
                   case L500: {
                     s.KFLAG = s.KFLAG - 1; s.n_efail++; s.TN = TOLD;
-                    VEC(i) {
-                      for (int JB = 1; JB <= s.NQ; ++JB)
-                        for (int j = s.NQ + 1 - JB; j <= s.NQ; ++j) YH(i, j) = YH(i, j) - YH(i, j + 1);
+#pragma unroll
+                    for (int JB = 1; JB <= 5; ++JB) {
+                      if (JB <= s.NQ) {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) { if (j >= s.NQ - JB && j < s.NQ) FORE yh[e][j] = yh[e][j] - yh[e][j + 1]; }
+                      }
                     }
-                    __syncthreads();
                     s.RMAX = 2.0;
                     if (fabs(s.H) <= s.HMIN * 1.00001) { pc = L660; break; }
                     if (s.KFLAG <= -3) { pc = L640; break; }
@@ -769,15 +1144,19 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                   case L520: {
                     RHUP = 0.0;
                     if (s.L == s.LMAX) { pc = L540; break; }
-                    VEC(i) sm.savf[i] = sm.acor[i] - YH(i, s.LMAX);
-                    DUP = wrms(sm.savf, sm.ewt, n, NEQ, sm.red) / net.tesco[s.NQ][3];
+                    DUP = wrms_reg([&](int e, int) { return acor[e] - yh[e][5]; }) / net.tesco[s.NQ][3];
                     RHUP = 1.0 / (1.4 * pow(DUP, 1.0 / (s.L + 1)) + 0.0000014);
                   }
                   case L540: {
                     RHSM = 1.0 / (1.2 * pow(DSM, 1.0 / s.L) + 0.0000012);
                     RHDN = 0.0;
                     if (s.NQ != 1) {
-                      DDN = wrms(&YH(0, s.L), sm.ewt, n, NEQ, sm.red) / net.tesco[s.NQ][1];
+                      const int Lc = s.L - 1;   // YH(:,L)
+                      DDN = wrms_reg([&](int e, int) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) if (j == Lc) v = yh[e][j];
+                        return v; }) / net.tesco[s.NQ][1];
                       RHDN = 1.0 / (1.3 * pow(DDN, 1.0 / s.NQ) + 0.0000013);
                     }
                     // labels 560-590
@@ -789,9 +1168,9 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                     else {
                       NEWQ = s.L; RH = RHUP;
                       if (RH < 1.1) { pc = L610; break; }
-                      R_ = s.EL[s.L] / s.L;
-                      VEC(i) YH(i, NEWQ + 1) = sm.acor[i] * R_;
-                      __syncthreads();
+                      R_ = (s.L == 2 ? s.EL2 : s.L == 3 ? s.EL3 : s.L == 4 ? s.EL4 : s.L == 5 ? s.EL5 : s.EL6) / s.L;
+#pragma unroll
+                      for (int j = 0; j < 6; ++j) { if (j == NEWQ) FORE yh[e][j] = acor[e] * R_; }   // YH(:,NEWQ+1)
                       pc = L630;
                     }
                     break;
@@ -813,14 +1192,13 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                     RH = 0.1;
                     RH = fmax(s.HMIN / fabs(s.H), RH);
                     s.H = s.H * RH;
-                    VEC(i) sm.y[i] = YH(i, 1);
                     __syncthreads();
+                    FORE sm.y[i] = yh[e][0];
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); eval_f(net, kx, fx, fx + R, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); __syncthreads(); eval_f(ks, fx, px, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
-                    VEC(i) YH(i, 2) = s.H * sm.savf[i];
-                    __syncthreads();
+                    FORE yh[e][1] = s.H * sm.savf[i];
                     s.IPUP = 1; s.IALTH = 5;
                     if (s.NQ == 1) { pc = L200; break; }
                     s.NQ = 1; s.L = 2; IRET = 3;
@@ -834,8 +1212,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
                     s.RMAX = 10.0;
                   case L700: {
                     R_ = 1.0 / net.tesco[s.NQU][2];
-                    VEC(i) sm.acor[i] = sm.acor[i] * R_;
-                    __syncthreads();
+                    FORE acor[e] = acor[e] * R_;
                     pc = L720;
                     break;
                   }
@@ -853,14 +1230,16 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
             case D_AFTER: {
               s.INIT = 1;
               if ((s.TN - TOUT) * s.H < 0.0) { dl = D345; break; }
-              dl = D_AFTER + 100;
+              dl = D_INTERP;
               break;
             }
-            case D_AFTER + 100: {   // DINTDY(TOUT, 0, ...) ; T = TOUT ; goto 420
+            case D_INTERP: {   // DINTDY(TOUT, 0, ...) ; T = TOUT ; goto 420
               const double S_ = (TOUT - s.TN) / s.H;
-              VEC(i) {
-                double v = YH(i, s.L);
-                for (int j = s.NQ; j >= 1; --j) v = YH(i, j) + S_ * v;
+              __syncthreads();
+              FORE {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 5; j >= 0; --j) { if (j == s.NQ) v = yh[e][j]; else if (j < s.NQ) v = yh[e][j] + S_ * v; }
                 sm.y[i] = v;
               }
               __syncthreads();
@@ -880,7 +1259,8 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
               break;
             }
             case D400: {
-              VEC(i) sm.y[i] = YH(i, 1);
+              __syncthreads();
+              FORE sm.y[i] = yh[e][0];
               __syncthreads();
               t = s.TN;
               if (s.IHIT) t = s.TCRIT;
@@ -890,7 +1270,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
             case D420: ISTATE = 2; dl = D_RET; break;
             case D560: {   // IMXER = first index of max |ACOR*EWT| (T slot contributes 0)
               double big = 0.0; int im = 0x7fffffff;
-              VEC(i) { const double sz = fabs(sm.acor[i] * sm.ewt[i]); if (sz > big) { big = sz; im = i; } }
+              FORE { const double sz = fabs(acor[e] * ewt[e]); if (sz > big) { big = sz; im = i; } }
               for (int o = 16; o > 0; o >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, big, o); const int oi = __shfl_xor_sync(0xffffffffu, im, o);
                 if (ob > big || (ob == big && oi < im)) { big = ob; im = oi; }
@@ -908,7 +1288,8 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
               break;
             }
             case D580: {
-              VEC(i) sm.y[i] = YH(i, 1);
+              __syncthreads();
+              FORE sm.y[i] = yh[e][0];
               __syncthreads();
               t = s.TN;
               dl = D_RET;
@@ -918,6 +1299,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
         }
       }
       // =================== back in chem_evol_solve ===================
+      __syncthreads();
       record_out(irec);
       n_record_real = irec;
       if (t >= t_max) break;
@@ -925,11 +1307,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
         NERR += 1; nerr_c += 1;
         if (ISTATE == -4 || ISTATE == -5) {   // ode_solver_error_handling, src/chemistry.f90:326-337
           const int idx = s.IMXER - 1;
-          if (tid == 0) {
-            ws.rtol[idx] = fmin(ws.rtol[idx] * 10.0, 1e-3);
-            ws.atol[idx] = fmin(ws.atol[idx] * 100.0, 1e-20);
-          }
-          __syncthreads();
+          FORE { if (i == idx) { rt[e] = fmin(rt[e] * 10.0, 1e-3); at[e] = fmin(at[e] * 100.0, 1e-20); } }
         }
         if (ISTATE == -7) { quality += 1024; break; }
         if (ISTATE == -3) { quality += 256; break; }
@@ -954,7 +1332,7 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
     if (NERR > (int)(0.1f * (float)n_record_formula)) quality += 1;
     if (t <= 0.5 * t_max) quality += 2;
     // ---- write results
-    VEC(i) args.y_final[(size_t)i * ncell + cell] = sm.y[i];
+    for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = sm.y[i];
     if (tid == 0) {
       args.y_final[(size_t)(NEQ - 1) * ncell + cell] = Tslot;
       args.t_final[cell] = t; args.nrec_real[cell] = n_record_real; args.istate[cell] = ISTATE;
@@ -969,34 +1347,38 @@ integrate_kernel(const DevNet net, const BatchArgs args) {
   }
   if (tid == 0 && args.phase) {
     ph[PH_TOTAL] = clock64() - tk0;
+#pragma unroll
     for (int k = 0; k < PH_COUNT; ++k) atomicAdd(&args.phase[k], ph[k]);
   }
-#undef YH
-#undef VEC
+#undef FORE
 }
 
-size_t integrate_smem_bytes(const DevNet& net, int npart_rhs, int npart_jac) {
-  const size_t n = net.n, R = net.R, nt = net.nt;
-  size_t V = 12 * n + 32 + 2 * NW;
-  size_t X = R + R + (size_t)npart_rhs;
-  X = X > R + 2 * R + (size_t)npart_jac ? X : R + 2 * R + (size_t)npart_jac;
-  size_t X3 = (size_t)NW * n + nt * nt;
-  X = X > X3 ? X : X3;
-  return (V + X) * sizeof(double);
+size_t integrate_smem_bytes(const DevNet& net) {
+  return make_layout(net).total * sizeof(double);
 }
 
 size_t integrate_ws_doubles(const DevNet& net) {
-  size_t w = (size_t)net.nJ + net.nslots + (size_t)net.nt * net.nt + net.R + 2 * (size_t)net.NEQ;
+  size_t w = (size_t)net.nstore + net.ubE.nval + net.lcE.nval + net.R + net.n_hh + net.n_ub;
   return (w + 15) & ~(size_t)15;
 }
 
 cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nblocks, size_t smem,
                              cudaStream_t stream) {
-  static bool attr_set = false;
-  cudaError_t e = cudaFuncSetAttribute(integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (net.nt > 16 * MAXTL || (net.nt & 15)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_net, &net, sizeof(DevNet), 0, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return e;
-  (void)attr_set;
-  integrate_kernel<<<nblocks, NT, smem, stream>>>(net, args);
+  const Layout L = make_layout(net);
+  const bool all = L.hh_smem && L.ub_smem;
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) return e2;
+    kern<<<nblocks, NT, smem, stream>>>(args);
+    return cudaSuccess;
+  };
+  if (net.n <= 2 * NT) e = all ? go(integrate_kernel<2, true>) : go(integrate_kernel<2, false>);
+  else if (net.n <= 3 * NT) e = all ? go(integrate_kernel<3, true>) : go(integrate_kernel<3, false>);
+  else e = go(integrate_kernel<4, false>);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

@@ -23,9 +23,10 @@ for rep in range(2):
 print("mean NST %.0f NFE %.0f NJE %.0f NLU %.0f nsolve %.0f ; max NST %.0f" % (st[:,0].mean(), st[:,1].mean(), st[:,2].mean(), st[:,3].mean(), st[:,5].mean(), st[:,0].max()))
 ph = sol.phase_cycles()
 tot = ph["total"]
-print("phase share of CTA cycles:", {k: round(v / tot, 4) for k, v in ph.items() if k not in ("total", "ncell")})
+print("phase share of CTA cycles:", {k: round(v / tot, 4) for k, v in ph.items() if k not in ("total", "ncell", "pbuild", "tail_inv")})
 print("cycles per cell (sum over CTAs / ncell): %.3e" % (tot / max(ph["ncell"], 1)))
 nlu, nsolve, nfe, nje, nst = st[:,3].sum(), st[:,5].sum(), st[:,1].sum(), st[:,2].sum(), st[:,0].sum()
+print("pbuild/LU %.0f tail_inv/LU %.0f" % (ph["pbuild"]/nlu, ph["tail_inv"]/nlu))
 print("cycles per op: LU %.0f (head %.0f schur %.0f tail %.0f) solve %.0f f %.0f jac %.0f vec/step %.0f" % (
     (ph["fact_head"]+ph["fact_schur"]+ph["fact_tail"])/nlu, ph["fact_head"]/nlu, ph["fact_schur"]/nlu, ph["fact_tail"]/nlu,
     ph["solve"]/nsolve, ph["f"]/nfe, ph["jac"]/nje, ph["vec"]/nst))
