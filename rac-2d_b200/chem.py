@@ -239,8 +239,8 @@ class ChemSolver:
         t0a = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, np.float64), (ncell,)))
         tma = np.ascontiguousarray(np.broadcast_to(np.asarray(t_max, np.float64), (ncell,)))
         dta = np.ascontiguousarray(np.broadcast_to(np.asarray(dt_first_step, np.float64), (ncell,)))
-        nrec = max(self.n_record(a, b, c, ratio_tstep) for a, b, c in
-                   set(zip(t0a.tolist(), tma.tolist(), dta.tolist())))
+        nrec = max([self.n_record(a, b, c, ratio_tstep) for a, b, c in
+                    set(zip(t0a.tolist(), tma.tolist(), dta.tolist()))] or [2])
         sp = SolveParams(ratio_tstep, mxstep_per_interval, steps_reset_solver, nrec, tol_policy_j, RTOL, ATOL)
         rt = _f(rtol) if rtol is not None else None
         at = _f(atol) if atol is not None else None
