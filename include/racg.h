@@ -26,6 +26,7 @@ extern "C" {
 
 #define RACG_NPAR 32     /* doubles per cell record (enum racg_par) */
 #define RACG_NSTAT 16    /* doubles per cell in stats */
+#define RACG_NPHASE 32   /* cycle counters returned by racg_phase_cycles */
 #define RACG_NAME_LEN 12 /* const_len_species_name, src/chemistry.f90:11 */
 #define RACG_NELEM 20    /* const_nElement, src/chemistry.f90:20 */
 
@@ -161,7 +162,7 @@ int racg_solve_batch_dev(racg_handle* h, int ncell, const double* cellpar, const
 /* number of kernel launches issued through this handle so far */
 long racg_launch_count(const racg_handle* h);
 /* per-phase SM-cycle counters of the last racg_solve_batch* call, summed over CTAs:
- * out[0..15]; returns 0 */
+ * out[0..RACG_NPHASE-1]; returns 0 */
 int racg_phase_cycles(racg_handle* h, double* out);
 
 #ifdef __cplusplus

@@ -11,7 +11,7 @@
 
 namespace racg {
 // racg_integrate.cu
-size_t integrate_smem_bytes(const DevNet& net);
+size_t integrate_smem_bytes(DevNet& net);
 size_t integrate_ws_doubles(const DevNet& net);
 cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nblocks, size_t smem, cudaStream_t stream);
 // racg_batch.cu
@@ -205,6 +205,22 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
   dn.flev_nfat_rows = hn.flev_ptr[hn.nfat_f]; dn.su_nfat_rows = hn.su_ptr[hn.nfat_b];
   dn.nflev = (int)hn.flev_ptr.size() - 1; dn.nfat_f = hn.nfat_f; UP(hn.flev_ptr, flev_ptr); UP(hn.flev_rows, flev_rows);
   dn.nsu = (int)hn.su_ptr.size() - 1; dn.nfat_b = hn.nfat_b; UP(hn.su_ptr, su_ptr); UP(hn.su_rows, su_rows);
+  {
+    const HostNet::LevelLU& g = hn.glu;
+    const HostNet::SolveSched& ss = hn.ss;
+    dn.glu.on = 0;
+    if (g.nlev > 0 && ss.nent > 0 && g.nlev <= GLU_MAXLEV && g.grp.size() / 4 <= (size_t)GLU_MAXGRP &&
+        ss.st.size() / 4 <= (size_t)SOLVE_MAXSTAGE && !getenv("RACG_NO_GLU")) {
+      dn.glu.on = 1; dn.glu.nlev = g.nlev; dn.glu.zpos = g.zpos;
+      UP(g.piv, glu.piv); UP(g.mul, glu.mul); UP(g.ent, glu.ent); UP(g.tgt, glu.tgt);
+      memcpy(dn.glu.lvl, g.lvl.data(), g.lvl.size() * sizeof(int));
+      memcpy(dn.glu.grp, g.grp.data(), g.grp.size() * sizeof(int));
+      dn.ss.nf = ss.nf; dn.ss.nb = ss.nb; dn.ss.nblkS = ss.nblkS; dn.ss.next = (int)ss.ext.size();
+      dn.ss.nent = ss.nent; dn.ss.nrp = ss.nrp; dn.ss.nrows = ss.nrows; dn.ss.blob_words = (int)ss.blob.size();
+      UP(ss.blob, ss.blob); UP(ss.ext, ss.ext);
+      memcpy(dn.ss.st, ss.st.data(), ss.st.size() * sizeof(int));
+    }
+  }
   dn.iH = hn.iH; dn.iE = hn.iE; dn.igH = hn.igH; dn.igH2 = hn.igH2; dn.igH2O = hn.igH2O;
   dn.iGrain0 = hn.iGrain0; dn.iGrainM = hn.iGrainM; dn.iGrainP = hn.iGrainP;
   UP(hn.hc_idx, hc_idx);
@@ -225,7 +241,7 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
   }
 #undef UP
   // integrator: one persistent CTA per SM, L2-resident workspace per CTA
-  h->smem_int = integrate_smem_bytes(dn);
+  h->smem_int = integrate_smem_bytes(dn);   // also plans the scratch region of the level-parallel mode
   if (h->smem_int > (size_t)prop.sharedMemPerBlockOptin)
     return fail(RACG_ERR_UNSUPPORTED, "network too large for the shared-memory layout of the integrator: " +
                                       std::to_string(h->smem_int) + " B needed");
@@ -234,8 +250,8 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
   CK(cudaMalloc(&h->d_ws, h->ws_stride * sizeof(double) * h->nblocks));
   CK(cudaMemset(h->d_ws, 0, h->ws_stride * sizeof(double) * h->nblocks));
   CK(cudaMalloc(&h->d_queue, sizeof(int)));
-  CK(cudaMalloc(&h->d_phase, 16 * sizeof(unsigned long long)));
-  CK(cudaMemset(h->d_phase, 0, 16 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_phase, RACG_NPHASE * sizeof(unsigned long long)));
+  CK(cudaMemset(h->d_phase, 0, RACG_NPHASE * sizeof(unsigned long long)));
   return 0;
 }
 
@@ -343,7 +359,7 @@ int racg_solve_batch_dev(racg_handle* h, int ncell, const double* cellpar, const
   a.nrec_real = nrec_real; a.istate = istate; a.quality = quality; a.stats = stats;
   a.queue = h->d_queue; a.ws = h->d_ws; a.ws_stride = h->ws_stride; a.phase = h->d_phase;
   CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), st));
-  CK(cudaMemsetAsync(h->d_phase, 0, 16 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(h->d_phase, 0, RACG_NPHASE * sizeof(unsigned long long), st));
   int nblocks = ncell < h->nblocks ? ncell : h->nblocks;
   CK(launch_integrate(h->dn, a, nblocks, h->smem_int, st));
   h->launches += 1;
@@ -437,9 +453,9 @@ long racg_launch_count(const racg_handle* h) { return h ? h->launches : 0; }
 
 int racg_phase_cycles(racg_handle* h, double* out) {
   int rc = need_gpu(h); if (rc) return rc;
-  unsigned long long v[16];
+  unsigned long long v[RACG_NPHASE];
   CK(cudaMemcpy(v, h->d_phase, sizeof(v), cudaMemcpyDeviceToHost));
-  for (int k = 0; k < 16; ++k) out[k] = (double)v[k];
+  for (int k = 0; k < RACG_NPHASE; ++k) out[k] = (double)v[k];
   return 0;
 }
 

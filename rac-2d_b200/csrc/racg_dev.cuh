@@ -27,6 +27,25 @@ struct EllDev {
   const int* comb_row; const int* comb_ptr;
 };
 
+// level-parallel factorisation schedule (HostNet::LevelLU); the per-level and per-group
+// descriptors sit in the constant-memory copy of DevNet so that the level loop never waits
+// on a dependent global load
+constexpr int GLU_MAXLEV = 127, GLU_MAXGRP = 640, SOLVE_MAXSTAGE = 64;
+struct GluDev {
+  int on, nlev, zpos, voff;
+  const uint32_t* piv; const uint32_t* mul; const uint32_t* ent; const uint16_t* tgt;
+  int4 lvl[GLU_MAXLEV + 1];   // {piv, mul, grp offsets, 0}
+  int4 grp[GLU_MAXGRP];       // {width, nblk, ent_off, tgt_off}
+};
+// staged head solves (HostNet::SolveSched)
+struct SolveDev {
+  int nf, nb, nblkS, next;
+  int nent, nrp, nrows, blob_words;
+  int xlow, sinv, tab;          // offsets (doubles) inside the scratch region X: see plan_glu()
+  const uint32_t* blob; const uint32_t* ext;
+  int4 st[SOLVE_MAXSTAGE];
+};
+
 struct DevNet {
   int R, N, NEQ, n, nh, nt, nsat, NNZ;
   // rates
@@ -54,6 +73,8 @@ struct DevNet {
   const int4* pivmeta;       // [nh]
   const int4* fmeta;         // [nh] forward-level order
   const int4* bmeta;         // [nh] backward-level order
+  GluDev glu;
+  SolveDev ss;
   // species of the sanity test (src/chemistry.f90:520-526), 0-based or -1
   int iH, iE, igH, igH2, igH2O, iGrain0, iGrainM, iGrainP;
   const int* hc_idx;         // [10]
@@ -84,7 +105,7 @@ struct BatchArgs {
   int* queue;                // work-queue counter
   double* ws;                // per-CTA workspace
   size_t ws_stride;          // doubles per CTA
-  unsigned long long* phase; // [16] cycle counters
+  unsigned long long* phase; // [RACG_NPHASE] cycle counters
 };
 
 // stand-alone K3 column-group schedule (racg_batch.cu)

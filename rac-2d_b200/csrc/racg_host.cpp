@@ -2,7 +2,9 @@
 #include "racg_host.hpp"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <cstdio>
 #include <map>
 #include <numeric>
 
@@ -309,12 +311,17 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   if (clique_start < 0) clique_start = n - 1;
   int nt0 = ((n - clique_start + 15) / 16) * 16;
   nt0 = std::max(16, std::min(std::min(nt0, 128), (n / 16) * 16));
+  // tuning overrides (diagnostics only): RACG_NT = dense-tail size, RACG_MULTI = ratio of
+  // the multiple-elimination rounds
+  double multi_ratio = 1.0;
+  if (const char* e = getenv("RACG_NT")) nt0 = std::max(16, std::min((atoi(e) / 16) * 16, (n / 16) * 16));
+  if (const char* e = getenv("RACG_MULTI")) multi_ratio = atof(e);
   std::vector<uint64_t> F;
   const size_t smem_budget = 227 * 1024 - 2048;
   bool placed = false;
   for (int nt = nt0; nt >= 16 && !placed; nt -= 16) {
     hn.nt = nt; hn.nh = n - nt;
-    hn.perm = min_degree_order(1.5, hn.nh, nullptr);
+    hn.perm = min_degree_order(multi_ratio, hn.nh, nullptr);
     symbolic(hn.perm, F);
     int n_hh = 0;
     for (int i = 0; i < hn.nh; ++i) for (int c = 0; c < hn.nh; ++c) if (getb(F, i, c) || c == i) ++n_hh;
@@ -359,7 +366,8 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     std::vector<std::vector<std::pair<int, int>>> rows(nrows);
     for (int i = 0; i < nrows; ++i) for (int q = ptr[i]; q < ptr[i + 1]; ++q) rows[i].push_back({q, 0});
     Gather g;
-    build_gather(g, rows, 32);
+    const int SEG = 16;    // sub-row length: one batch of loads per block in the solves
+    build_gather(g, rows, SEG);
     e.nblk = g.nblk; e.npartial = g.npartial; e.ncombine = g.ncombine;
     e.blk_off = g.blk_off; e.blk_width = g.blk_width; e.sub_target = g.sub_target;
     e.comb_row = g.comb_row; e.comb_ptr = g.comb_ptr;
@@ -375,7 +383,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
       std::vector<Sub> subs;
       for (int r = 0; r < nrows; ++r) {
         int len = (int)rows[r].size();
-        for (int f = 0; f < len; f += 32) subs.push_back({r, f, std::min(32, len - f)});
+        for (int f = 0; f < len; f += SEG) subs.push_back({r, f, std::min(SEG, len - f)});
       }
       std::stable_sort(subs.begin(), subs.end(), [](const Sub& x, const Sub& y) { return x.len > y.len; });
       for (size_t s = 0; s < subs.size(); ++s) {
@@ -511,6 +519,167 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
       int r = hn.ja[k] - 1;
       if (r < n) hn.csc_to_store[k] = store_index(hn.iperm[r], hn.iperm[c]);
     }
+  // ---- level-parallel factorisation schedule (HostNet::LevelLU) and staged solves
+  if (hn.nstore + 1 < 65535) {
+    HostNet::LevelLU& g = hn.glu;
+    g.zpos = hn.nstore;
+    std::vector<int> lev(nh, 0);
+    for (int k = 0; k < nh; ++k) {
+      int l = 0;
+      for (int c = 0; c < k; ++c) if (getb(F, k, c) || getb(F, c, k)) l = std::max(l, lev[c] + 1);
+      lev[k] = l;
+    }
+    g.nlev = 0;
+    for (int k = 0; k < nh; ++k) g.nlev = std::max(g.nlev, lev[k] + 1);
+    std::vector<std::vector<int>> members(g.nlev);
+    for (int k = 0; k < nh; ++k) members[lev[k]].push_back(k);
+    bool ok = true;
+    for (int L = 0; L < g.nlev && ok; ++L) {
+      g.lvl.insert(g.lvl.end(), {(int)g.piv.size(), (int)g.mul.size(), (int)g.grp.size() / 4, 0});
+      std::map<int, std::vector<uint32_t>> upd;     // target position -> pairs
+      for (int k : members[L]) {
+        g.piv.push_back((uint32_t)store_index(k, k) | ((uint32_t)k << 16));
+        std::vector<int> cols;
+        for (int j = k + 1; j < n; ++j) if (getb(F, k, j)) cols.push_back(j);
+        for (int i = k + 1; i < n; ++i) {
+          if (!getb(F, i, k)) continue;
+          const int pl = store_index(i, k);
+          g.mul.push_back((uint32_t)pl | ((uint32_t)k << 16));
+          for (int j : cols) {
+            const int pt = store_index(i, j), pu = store_index(k, j);
+            if (pt < 0 || pu < 0 || pl < 0) { ok = false; break; }
+            upd[pt].push_back((uint32_t)pl | ((uint32_t)pu << 16));
+          }
+        }
+      }
+      std::vector<std::pair<int, int>> order;   // (-count, target)
+      for (auto& kv : upd) { order.push_back({-(int)kv.second.size(), kv.first}); g.npairs += (long)kv.second.size(); }
+      std::sort(order.begin(), order.end());
+      // blocks of 32 targets; consecutive blocks of equal width form a group
+      for (size_t s0 = 0; s0 < order.size(); s0 += 32) {
+        const int width = -order[s0].first;
+        const size_t ng = g.grp.size();
+        if (ng == (size_t)4 * g.lvl[g.lvl.size() - 2] || g.grp[ng - 4] != width)
+          g.grp.insert(g.grp.end(), {width, 0, (int)g.ent.size(), (int)g.tgt.size()});
+        g.grp[g.grp.size() - 3] += 1;
+        const size_t off = g.ent.size();
+        g.ent.resize(off + (size_t)width * 32, (uint32_t)g.zpos | ((uint32_t)g.zpos << 16));
+        for (int l = 0; l < 32; ++l) {
+          if (s0 + l >= order.size()) { g.tgt.push_back(0xFFFF); continue; }
+          const int t = order[s0 + l].second;
+          g.tgt.push_back((uint16_t)t);
+          const auto& pr = upd[t];
+          for (size_t j = 0; j < pr.size(); ++j) g.ent[off + j * 32 + l] = pr[j];
+        }
+      }
+    }
+    g.lvl.insert(g.lvl.end(), {(int)g.piv.size(), (int)g.mul.size(), (int)g.grp.size() / 4, 0});
+    if (!ok) g = HostNet::LevelLU();
+    if (ok) {
+      HostNet::SolveSched& ss = hn.ss;
+      // S: the longest suffix of levels holding <= 96 rows
+      int thr = g.nlev, cnt = 0;
+      while (thr > 0 && cnt + (int)members[thr - 1].size() <= 96) { cnt += (int)members[thr - 1].size(); --thr; }
+      std::vector<int> Srows, blkOf(nh, -1), locOf(nh, 0);
+      for (int k = 0; k < nh; ++k) if (lev[k] >= thr) Srows.push_back(k);
+      ss.nblkS = ((int)Srows.size() + 31) / 32;
+      for (size_t q = 0; q < Srows.size(); ++q) { blkOf[Srows[q]] = (int)(q / 32); locOf[Srows[q]] = (int)(q % 32); }
+      std::vector<uint32_t> t_ent; std::vector<uint16_t> t_rp, t_rows;
+      auto add_stage = [&](int kind, const std::vector<int>& rows, const std::vector<std::vector<uint32_t>>& ents, int inv) {
+        const int nrows = (int)rows.size();
+        int maxlen = 0;
+        for (auto& e : ents) maxlen = std::max(maxlen, (int)e.size());
+        int lg;
+        if (kind == 2) lg = 3;
+        else { lg = 5; while (lg > 0 && (nrows << lg) > 256) --lg; while (lg > 0 && (1 << (lg - 1)) >= std::max(1, maxlen)) --lg; }
+        const int row_off = (int)t_rows.size(), rp_off = (int)t_rp.size();
+        for (int r = 0; r < nrows; ++r) {
+          t_rows.push_back((uint16_t)rows[r]);
+          t_rp.push_back((uint16_t)t_ent.size());
+          for (uint32_t e : ents[r]) t_ent.push_back(e);
+        }
+        t_rp.push_back((uint16_t)t_ent.size());
+        ss.st.insert(ss.st.end(), {kind | (lg << 8), nrows | (inv << 16), row_off, rp_off});
+      };
+      auto row_entries = [&](int i, bool upper, int skip_blk) {
+        std::vector<uint32_t> e;
+        const int b0 = upper ? hn.hh_ptr[i] + hn.hh_nl[i] + 1 : hn.hh_ptr[i];
+        const int b1 = upper ? hn.hh_ptr[i + 1] : hn.hh_ptr[i] + hn.hh_nl[i];
+        for (int q = b0; q < b1; ++q) {
+          const int c = hn.hh_col[q];
+          if (skip_blk >= 0 && blkOf[c] == skip_blk) continue;
+          e.push_back((uint32_t)q | ((uint32_t)c << 16));
+        }
+        return e;
+      };
+      auto add_level = [&](int kind, const std::vector<int>& rows, bool upper) {
+        for (size_t r0 = 0; r0 < rows.size(); r0 += 256) {
+          std::vector<int> rr(rows.begin() + r0, rows.begin() + std::min(rows.size(), r0 + 256));
+          std::vector<std::vector<uint32_t>> ee;
+          for (int i : rr) ee.push_back(row_entries(i, upper, -1));
+          add_stage(kind, rr, ee, 0);
+        }
+      };
+      auto add_block = [&](int b, bool upper) {
+        std::vector<int> rr(Srows.begin() + 32 * b, Srows.begin() + std::min<size_t>(Srows.size(), 32 * b + 32));
+        std::vector<std::vector<uint32_t>> ee;
+        for (int i : rr) ee.push_back(row_entries(i, upper, b));
+        add_stage(2, rr, ee, b);
+      };
+      // forward: levels 1..thr-1 (level 0 has nothing to subtract), then the S blocks
+      for (int L = 1; L < thr; ++L) add_level(0, members[L], false);
+      for (int b = 0; b < ss.nblkS; ++b) add_block(b, false);
+      ss.nf = (int)ss.st.size() / 4;
+      // backward: S blocks in reverse, then the other rows by their depth below S
+      for (int b = ss.nblkS - 1; b >= 0; --b) add_block(b, true);
+      {
+        std::vector<int> bl(nh, 0);
+        int nbl = 0;
+        for (int i = nh - 1; i >= 0; --i) {
+          if (blkOf[i] >= 0) continue;
+          int l = 0;
+          for (int q = hn.hh_ptr[i] + hn.hh_nl[i] + 1; q < hn.hh_ptr[i + 1]; ++q) {
+            const int c = hn.hh_col[q];
+            if (blkOf[c] < 0) l = std::max(l, bl[c] + 1);
+          }
+          bl[i] = l; nbl = std::max(nbl, l + 1);
+        }
+        std::vector<std::vector<int>> bm(nbl);
+        for (int i = 0; i < nh; ++i) if (blkOf[i] < 0) bm[bl[i]].push_back(i);
+        for (int L = 0; L < nbl; ++L) add_level(1, bm[L], true);
+      }
+      ss.nb = (int)ss.st.size() / 4 - ss.nf;
+      // dense copies of the S diagonal blocks: unit-lower part -> tile 2b, upper part -> tile 2b+1
+      for (int i : Srows)
+        for (int q = hn.hh_ptr[i]; q < hn.hh_ptr[i + 1]; ++q) {
+          const int c = hn.hh_col[q];
+          if (blkOf[c] != blkOf[i]) continue;
+          ss.ext.push_back((uint32_t)q | ((uint32_t)(blkOf[i] * 33 * 32 + locOf[c] * 33 + locOf[i]) << 16));
+        }
+      // one blob the kernel stages into shared memory: entries | row pointers | row ids
+      if (t_ent.size() >= 65535) { hn.glu = HostNet::LevelLU(); ss = HostNet::SolveSched(); }
+      else {
+        ss.nent = (int)t_ent.size(); ss.nrp = (int)t_rp.size(); ss.nrows = (int)t_rows.size();
+        ss.blob = t_ent;
+        auto pack16 = [&](const std::vector<uint16_t>& v) {
+          for (size_t q = 0; q < v.size(); q += 2)
+            ss.blob.push_back((uint32_t)v[q] | ((q + 1 < v.size() ? (uint32_t)v[q + 1] : 0u) << 16));
+        };
+        pack16(t_rp); pack16(t_rows);
+      }
+    }
+  }
+  if (getenv("RACG_VERBOSE")) {
+    fprintf(stderr, "racg: n=%d nh=%d nt=%d n_hh=%d n_ub=%d n_lc=%d nstore=%d nnz_lu=%d flev=%d su=%d | glu: nlev=%d "
+            "pairs=%ld ent=%zu mul=%zu groups=%zu | solve stages fwd=%d bwd=%d blocksS=%d ent=%d blob=%zu words | "
+            "ELL blocks U_B %d L_C %d:", n, nh, nt,
+            hn.n_hh, hn.n_ub, hn.n_lc, hn.nstore, hn.nnz_lu, (int)hn.flev_ptr.size() - 1,
+            (int)hn.su_ptr.size() - 1, hn.glu.nlev, hn.glu.npairs, hn.glu.ent.size(), hn.glu.mul.size(),
+            hn.glu.grp.size() / 4, hn.ss.nf, hn.ss.nb, hn.ss.nblkS, hn.ss.nent, hn.ss.blob.size(), hn.ubE.nblk, hn.lcE.nblk);
+    for (size_t q = 0; q < hn.ss.st.size(); q += 4)
+      fprintf(stderr, " [k%d lpr%d r%d]", hn.ss.st[q] & 255, 1 << ((hn.ss.st[q] >> 8) & 255), hn.ss.st[q + 1] & 0xffff);
+    fprintf(stderr, "\n");
+  }
   // ---- stand-alone K3 schedule: columns grouped so that a group's partial
   // derivatives fit the shared-memory buffer; hub columns are cut into chunks that
   // accumulate into pd.

@@ -96,6 +96,37 @@ struct HostNet {
   //   fmeta[pos]  = {row, start of L_A(row,:) in hh, its length, 0}   in forward-level order
   //   bmeta[pos]  = {row, start of U_A(row,:) in hh, its length, 0}   in backward-level order
   std::vector<int> pivmeta, fmeta, bmeta;
+  // ---- level-parallel numeric factorisation ("gather LU", racg_integrate.cu factor_glu):
+  // head pivots are grouped into levels whose members neither update nor read one another;
+  // for one level every multiplier l(i,k) = a(i,k)/a(k,k) and then every updated entry
+  // a(i,j) -= sum_k l(i,k) u(k,j) is independent, so the schedule lists per target the
+  // (position of l, position of u) pairs, packed as 32-lane ELL blocks.
+  struct LevelLU {
+    int nlev = 0, zpos = 0;
+    long npairs = 0;
+    std::vector<int> lvl;                               // int4 per level (+1 sentinel): {piv, mul, grp offsets, 0}
+    std::vector<int> grp;                               // int4 per group: {width, nblk, ent_off, tgt_off}
+    std::vector<uint32_t> piv;                          // diag position | pivot row << 16
+    std::vector<uint32_t> mul;                          // position of a(i,k) | k << 16
+    std::vector<uint16_t> tgt;                          // [32 per block] target position, 0xFFFF = idle
+    std::vector<uint32_t> ent;                          // pos_l | pos_u << 16 (padding: zpos twice);
+                                                        // entry j of lane l of block b of a group at
+                                                        // ent_off + (b*width + j)*32 + l
+  } glu;
+  // ---- staged triangular solves of the head block (racg_integrate.cu solve_glu).  The last
+  // <= 96 head rows (deepest levels: a nearly dense chain) form 32-row blocks S whose diagonal
+  // blocks are inverted explicitly after every factorisation; everything else goes level by
+  // level.  A stage is one pass of 256 threads: row r = tid / lpr gathers
+  // sum V[pos] * x[col] over its entries (lane tid % lpr takes every lpr-th one); the tables
+  // are small enough to live in shared memory between factorisations.
+  struct SolveSched {
+    int nf = 0, nb = 0, nblkS = 0, nent = 0, nrp = 0, nrows = 0;
+    std::vector<int> st;           // int4 per stage: {kind | log2(lpr)<<8, nrows | block<<16, row_off, rp_off}
+                                   // kind 0: x = b - acc; 1: x = (b - acc) / pivot; 2: x_blk = Inv[block] (b - acc)
+    std::vector<uint32_t> blob;    // [nent] entries pos | col<<16, then row pointers (u16 pairs), then row ids
+    std::vector<uint32_t> ext;     // S diagonal blocks: pos | tile offset << 16 (tile = b*33*32 + c*33 + r)
+  } ss;
+
   // ---- Jacobian gather into the storage index space, two passes (d/dy_r1, d/dy_r2) ----
   Gather jac[2];
   // map from the user's CSC slot (ia/ja) to the storage index or -1

