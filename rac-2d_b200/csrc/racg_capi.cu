@@ -209,16 +209,20 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
     const HostNet::LevelLU& g = hn.glu;
     const HostNet::SolveSched& ss = hn.ss;
     dn.glu.on = 0;
-    if (g.nlev > 0 && ss.nent > 0 && g.nlev <= GLU_MAXLEV && g.grp.size() / 4 <= (size_t)GLU_MAXGRP &&
-        ss.st.size() / 4 <= (size_t)SOLVE_MAXSTAGE && !getenv("RACG_NO_GLU")) {
+    if (g.nlev > 0 && ss.nent > 0 && !getenv("RACG_NO_GLU")) {
       dn.glu.on = 1; dn.glu.nlev = g.nlev; dn.glu.zpos = g.zpos;
       UP(g.piv, glu.piv); UP(g.mul, glu.mul); UP(g.ent, glu.ent); UP(g.tgt, glu.tgt);
-      memcpy(dn.glu.lvl, g.lvl.data(), g.lvl.size() * sizeof(int));
-      memcpy(dn.glu.grp, g.grp.data(), g.grp.size() * sizeof(int));
+      std::vector<int> desc(g.lvl);
+      desc.insert(desc.end(), g.grp.begin(), g.grp.end());
+      desc.insert(desc.end(), ss.st.begin(), ss.st.end());
+      desc.insert(desc.end(), g.r1.begin(), g.r1.end());
+      dn.glu.nst = (int)ss.st.size() / 4;
+      UP(g.r1tgt, glu.r1tgt);
+      dn.glu.ngrp = (int)g.grp.size() / 4; dn.glu.ndesc = (int)desc.size() / 4;
+      { const int* p; if ((rc = upload(h, desc, &p))) return rc; dn.glu.desc = (const int4*)p; }
       dn.ss.nf = ss.nf; dn.ss.nb = ss.nb; dn.ss.nblkS = ss.nblkS; dn.ss.next = (int)ss.ext.size();
       dn.ss.nent = ss.nent; dn.ss.nrp = ss.nrp; dn.ss.nrows = ss.nrows; dn.ss.blob_words = (int)ss.blob.size();
       UP(ss.blob, ss.blob); UP(ss.ext, ss.ext);
-      memcpy(dn.ss.st, ss.st.data(), ss.st.size() * sizeof(int));
     }
   }
   dn.iH = hn.iH; dn.iE = hn.iE; dn.igH = hn.igH; dn.igH2 = hn.igH2; dn.igH2O = hn.igH2O;

@@ -30,20 +30,23 @@ struct EllDev {
 // level-parallel factorisation schedule (HostNet::LevelLU); the per-level and per-group
 // descriptors sit in the constant-memory copy of DevNet so that the level loop never waits
 // on a dependent global load
-constexpr int GLU_MAXLEV = 127, GLU_MAXGRP = 640, SOLVE_MAXSTAGE = 64;
+// level-parallel factorisation schedule (HostNet::LevelLU) and staged head solves
+// (HostNet::SolveSched).  The int4 descriptors (levels, groups, stages) are staged into
+// shared memory once per CTA: the level loop must never wait on a dependent global or
+// constant-cache miss.
 struct GluDev {
   int on, nlev, zpos, voff;
+  int ngrp, ndesc, doff;      // descriptor block: [lvl (nlev+1) | grp (ngrp) | stages (nst) | rank-1 pairs]; doff = offset in smem (doubles)
   const uint32_t* piv; const uint32_t* mul; const uint32_t* ent; const uint16_t* tgt;
-  int4 lvl[GLU_MAXLEV + 1];   // {piv, mul, grp offsets, 0}
-  int4 grp[GLU_MAXGRP];       // {width, nblk, ent_off, tgt_off}
+  const uint16_t* r1tgt;      // rank-1 levels: 4 target positions per (row chunk, column chunk, lane)
+  int nst;                    // number of solve stages (descriptors follow the groups, then the rank-1 pairs)
+  const int4* desc;           // lvl: {piv, mul, grp offsets, rank-1 index or -1}; grp: {width, nblk, ent_off, tgt_off}
 };
-// staged head solves (HostNet::SolveSched)
 struct SolveDev {
   int nf, nb, nblkS, next;
   int nent, nrp, nrows, blob_words;
-  int xlow, sinv, tab;          // offsets (doubles) inside the scratch region X: see plan_glu()
+  int xlow, sinv, tab;          // offsets (doubles) inside the scratch region X: see integrate_smem_bytes()
   const uint32_t* blob; const uint32_t* ext;
-  int4 st[SOLVE_MAXSTAGE];
 };
 
 struct DevNet {

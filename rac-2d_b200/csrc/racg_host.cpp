@@ -520,7 +520,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
       if (r < n) hn.csc_to_store[k] = store_index(hn.iperm[r], hn.iperm[c]);
     }
   // ---- level-parallel factorisation schedule (HostNet::LevelLU) and staged solves
-  if (hn.nstore + 1 < 65535) {
+  if (hn.nstore + 2 < 65535) {
     HostNet::LevelLU& g = hn.glu;
     g.zpos = hn.nstore;
     std::vector<int> lev(nh, 0);
@@ -535,7 +535,36 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     for (int k = 0; k < nh; ++k) members[lev[k]].push_back(k);
     bool ok = true;
     for (int L = 0; L < g.nlev && ok; ++L) {
-      g.lvl.insert(g.lvl.end(), {(int)g.piv.size(), (int)g.mul.size(), (int)g.grp.size() / 4, 0});
+      const bool rank1 = members[L].size() == 1;
+      g.lvl.insert(g.lvl.end(), {(int)g.piv.size(), (int)g.mul.size(), (int)g.grp.size() / 4,
+                                 rank1 ? (int)g.r1.size() / 8 : -1});
+      if (rank1) {
+        const int k = members[L][0];
+        g.piv.push_back((uint32_t)store_index(k, k) | ((uint32_t)k << 16));
+        std::vector<int> rws, cols;
+        for (int i = k + 1; i < n; ++i) if (getb(F, i, k)) rws.push_back(i);
+        const int ua0 = hn.hh_ptr[k] + hn.hh_nl[k] + 1, nua = hn.hh_ptr[k + 1] - ua0;
+        const int ub0 = hn.o_ub + hn.ub_ptr[k], nub = hn.ub_ptr[k + 1] - hn.ub_ptr[k];
+        const int nua4 = (nua + 3) / 4, nub4 = (nub + 3) / 4, nj4 = nua4 + nub4;
+        // column of chunk j4, slot c (permuted index) or -1 for padding
+        auto col_of = [&](int j4, int c) -> int {
+          if (j4 < nua4) { int q = 4 * j4 + c; return q < nua ? (int)hn.hh_col[ua0 + q] : -1; }
+          int q = 4 * (j4 - nua4) + c; return q < nub ? nh + (int)hn.ub_col[hn.ub_ptr[k] + q] : -1;
+        };
+        for (int i : rws) g.mul.push_back((uint32_t)store_index(i, k) | ((uint32_t)store_index(k, k) << 16));
+        const int nr = (int)rws.size(), nrc = (nr + 31) / 32;
+        g.r1.insert(g.r1.end(), {ua0, nua4, ub0, nub4, (int)(g.r1tgt.size() / 4), nr, nj4, 0});
+        for (int rc = 0; rc < nrc; ++rc)
+          for (int j4 = 0; j4 < nj4; ++j4)
+            for (int l = 0; l < 32; ++l)
+              for (int c = 0; c < 4; ++c) {
+                const int m = rc * 32 + l, j = col_of(j4, c);
+                int t = g.zpos + 1;
+                if (m < nr && j >= 0) { t = store_index(rws[m], j); if (t < 0) ok = false; ++g.npairs; }
+                g.r1tgt.push_back((uint16_t)t);
+              }
+        continue;
+      }
       std::map<int, std::vector<uint32_t>> upd;     // target position -> pairs
       for (int k : members[L]) {
         g.piv.push_back((uint32_t)store_index(k, k) | ((uint32_t)k << 16));
@@ -544,7 +573,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
         for (int i = k + 1; i < n; ++i) {
           if (!getb(F, i, k)) continue;
           const int pl = store_index(i, k);
-          g.mul.push_back((uint32_t)pl | ((uint32_t)k << 16));
+          g.mul.push_back((uint32_t)pl | ((uint32_t)store_index(k, k) << 16));
           for (int j : cols) {
             const int pt = store_index(i, j), pu = store_index(k, j);
             if (pt < 0 || pu < 0 || pl < 0) { ok = false; break; }
@@ -678,6 +707,8 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
             hn.glu.grp.size() / 4, hn.ss.nf, hn.ss.nb, hn.ss.nblkS, hn.ss.nent, hn.ss.blob.size(), hn.ubE.nblk, hn.lcE.nblk);
     for (size_t q = 0; q < hn.ss.st.size(); q += 4)
       fprintf(stderr, " [k%d lpr%d r%d]", hn.ss.st[q] & 255, 1 << ((hn.ss.st[q] >> 8) & 255), hn.ss.st[q + 1] & 0xffff);
+    fprintf(stderr, "\nracg: rank-1 levels %zu, target slots %zu; (nr,nc) per level:", hn.glu.r1.size() / 8, hn.glu.r1tgt.size());
+    for (size_t q = 0; q < hn.glu.r1.size(); q += 8) fprintf(stderr, " (%d,%d)", hn.glu.r1[q + 5], 4 * hn.glu.r1[q + 6]);
     fprintf(stderr, "\n");
   }
   // ---- stand-alone K3 schedule: columns grouped so that a group's partial

@@ -106,8 +106,16 @@ struct HostNet {
     long npairs = 0;
     std::vector<int> lvl;                               // int4 per level (+1 sentinel): {piv, mul, grp offsets, 0}
     std::vector<int> grp;                               // int4 per group: {width, nblk, ent_off, tgt_off}
+    // single-pivot levels ("rank-1 levels": the nearly dense chain at the end of the head) are
+    // done as an outer product rows(k) x cols(k) instead: lvl.w = index of the level's
+    // descriptor pair in r1 (-1 otherwise): {ua0, nua4, ub0, nub4}, {tgt_off, nr, nj4, 0};
+    // rows = the level's multipliers in order, cols = U(k,:) in storage order (head part and
+    // tail part each padded to a multiple of 4); r1tgt holds 4 target positions per
+    // (row chunk of 32, column chunk of 4, lane), padded with the trash slot zpos + 1
+    std::vector<int> r1;
+    std::vector<uint16_t> r1tgt;
     std::vector<uint32_t> piv;                          // diag position | pivot row << 16
-    std::vector<uint32_t> mul;                          // position of a(i,k) | k << 16
+    std::vector<uint32_t> mul;                          // position of a(i,k) | position of a(k,k) << 16
     std::vector<uint16_t> tgt;                          // [32 per block] target position, 0xFFFF = idle
     std::vector<uint32_t> ent;                          // pos_l | pos_u << 16 (padding: zpos twice);
                                                         // entry j of lane l of block b of a group at

@@ -156,30 +156,38 @@ __device__ __forceinline__ void run_gather(const GatherDev& g, const double* src
                                            double* partial) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int b = w; b < g.nblk; b += NW) {
-    const int off = g.blk_off[b], width = g.blk_width[b];
-    const uint32_t* e = g.ent + off + l;
+    const int width = __ldg(g.blk_width + b);
+    const uint32_t* e = g.ent + __ldg(g.blk_off + b) + l;
     uint32_t ev[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) ev[j] = (j < width) ? __ldcs(e + j * 32) : (4u << 24);
-    double acc = 0.0;
+    for (int j = 0; j < 32; ++j) ev[j] = (j < width) ? __ldcg(e + j * 32) : (4u << 24);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < width) {
-        const int c = (int)(ev[j] >> 24) - 4;
-        const double s = src[ev[j] & 0xffffffu];
-        acc += (c != 0) ? (double)c * s : 0.0;
+    for (int j0 = 0; j0 < 32; j0 += 8) {
+      if (j0 < width) {
+        double sv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sv[j] = src[ev[j0 + j] & 0xffffffu];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = (int)(ev[j0 + j] >> 24) - 4;
+          acc[j & 3] += (c != 0) ? (double)c * sv[j] : 0.0;
+        }
       }
     }
-    const int t = g.sub_target[b * 32 + l];
+    const double a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const int t = __ldg(g.sub_target + b * 32 + l);
     if (t >= 0) {
-      if (GLOBAL_OUT && g.sub_add && g.sub_add[b * 32 + l]) out[t] += acc; else out[t] = acc;
-    } else if (t <= -2) partial[-2 - t] = acc;
+      if (GLOBAL_OUT && g.sub_add && g.sub_add[b * 32 + l]) out[t] += a; else out[t] = a;
+    } else if (t <= -2) partial[-2 - t] = a;
   }
   __syncthreads();
   for (int q = threadIdx.x; q < g.ncombine; q += NT) {
     double s = 0.0;
-    for (int p = g.comb_ptr[q]; p < g.comb_ptr[q + 1]; ++p) s += partial[p];
-    if (GLOBAL_OUT && g.comb_add && g.comb_add[q]) out[g.comb_row[q]] += s; else out[g.comb_row[q]] = s;
+    const int p0 = __ldg(g.comb_ptr + q), p1 = __ldg(g.comb_ptr + q + 1);
+    for (int p = p0; p < p1; ++p) s += partial[p];
+    const int row = __ldg(g.comb_row + q);
+    if (GLOBAL_OUT && g.comb_add && g.comb_add[q]) out[row] += s; else out[row] = s;
   }
   __syncthreads();
 }
@@ -231,20 +239,24 @@ __device__ __forceinline__ double dflux_of(uint32_t w, double k, const double* y
   return 0.0;
 }
 
-// chem_ode_f: out = S * flux(k, yv).  k streamed from the workspace (L2), fluxes in X
-__device__ __forceinline__ void eval_f(const double* __restrict__ ks, double* fx,
-                                       double* px, const double* yv, double* out, double DS,
-                                       unsigned long long* ph) {
+// chem_ode_f: savf = S * flux(k, y).  k streamed from the workspace (L2), fluxes in the
+// scratch region X (x_off = its offset in the shared-memory block); y = smem_raw[0..n),
+// savf = smem_raw[n..2n)
+__device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off, double DS, unsigned long long* ph) {
   const DevNet& net = c_net;
   const int R = net.R;
-  __syncthreads();   // yv was just written by its owner threads
+  double* const fx = smem_raw + x_off;
+  double* const px = fx + R;
+  const double* const yv = smem_raw;
+  double* const out = smem_raw + net.n;
+  __syncthreads();   // y was just written by its owner threads
   const long long tf0 = clock64();
   for (int r0 = threadIdx.x; r0 < R; r0 += 4 * NT) {
     double kk[4]; uint32_t ww[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int r = r0 + u * NT;
-      kk[u] = (r < R) ? __ldcs(ks + r) : 0.0;
+      kk[u] = (r < R) ? __ldcg(ks + r) : 0.0;
       ww[u] = (r < R) ? __ldg(net.fw + r) : 0u;
     }
 #pragma unroll
@@ -261,12 +273,14 @@ __device__ __forceinline__ void eval_f(const double* __restrict__ ks, double* fx
 }
 
 // chem_ode_jac for all columns at once -> ws.J (two passes over the reactions)
-__device__ __forceinline__ void eval_jac(const double* __restrict__ ks, double* dfx,
-                                         double* px, const double* yv, double* J, double DS) {
+__device__ __forceinline__ void eval_jac(const double* __restrict__ ks, int x_off, double* J, double DS) {
   const DevNet& net = c_net;
+  double* const dfx = smem_raw + x_off;
+  double* const px = dfx + net.R;
+  const double* const yv = smem_raw;
   __syncthreads();
   for (int pass = 0; pass < 2; ++pass) {
-    for (int r = threadIdx.x; r < net.R; r += NT) dfx[r] = dflux_of(__ldg(net.fw + r), __ldcs(ks + r), yv, DS, pass);
+    for (int r = threadIdx.x; r < net.R; r += NT) dfx[r] = dflux_of(__ldg(net.fw + r), __ldcg(ks + r), yv, DS, pass);
     __syncthreads();
     run_gather<true>(net.jac[pass], dfx, J, px);
   }
@@ -409,12 +423,13 @@ __device__ __noinline__ void tail_block_inverses(Smem sm) {
 // ---------------------------------------------------------------------------
 // Shared-memory view of the level-parallel mode, derived from the smem_raw symbol so that
 // every access below is a shared-space access.
-struct GSm { double *y, *xb, *dinv, *V, *X, *Dt; };
+struct GSm { double *y, *xb, *dinv, *V, *X, *Dt; const int4 *lvl, *grp, *st, *r1; };
 __device__ __forceinline__ GSm glu_smem() {
   const DevNet& net = c_net;
   GSm g;
   g.y = smem_raw; g.xb = smem_raw + net.n; g.dinv = smem_raw + 2 * net.n;
   g.V = smem_raw + net.glu.voff; g.X = g.V + net.o_ub; g.Dt = g.V + net.o_tl;
+  g.lvl = (const int4*)(smem_raw + net.glu.doff); g.grp = g.lvl + net.glu.nlev + 1; g.st = g.grp + net.glu.ngrp; g.r1 = g.st + net.glu.nst;
   return g;
 }
 
@@ -425,27 +440,57 @@ __device__ __forceinline__ GSm glu_smem() {
 // block share a scratch tile: their triangles are disjoint and the L job never touches the
 // diagonal (z_j = 1 is implicit).
 __device__ __forceinline__ void tri_inv_lower(const double* src, int ld, int bs, int j, double* zs) {
-  for (int i = j + 1; i < bs; ++i) zs[i * 33 + j] = 0.0;
-  for (int k = 0; k + 1 < bs; ++k) {
-    const double zl = zs[k * 33 + j];
-    const double zk = (k < j) ? 0.0 : ((k == j) ? 1.0 : zl);
-    const double* lk = src + k * ld;
-#pragma unroll 4
-    for (int i = k + 1; i < bs; ++i)
-      if (i > j && k >= j) zs[i * 33 + j] -= lk[i] * zk;
+  // rows in chunks of 8 held in registers: first the contributions of all earlier rows k
+  // (z_k final), then the 8x8 triangle of the chunk itself
+  for (int R0 = 0; R0 < bs; R0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+    for (int k = 0; k < R0; ++k) {
+      const double zl = zs[k * 33 + j];
+      const double zk = (k < j) ? 0.0 : ((k == j) ? 1.0 : zl);
+      const double* lk = src + k * ld + R0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] -= lk[r] * zk;
+    }
+    double z[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = R0 + r;
+      double v = acc[r];
+#pragma unroll
+      for (int r2 = 0; r2 < r; ++r2) v -= src[(R0 + r2) * ld + i] * z[r2];
+      z[r] = (i < j) ? 0.0 : ((i == j) ? 1.0 : v);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (R0 + r > j) zs[(R0 + r) * 33 + j] = z[r];
   }
 }
 __device__ __forceinline__ void tri_inv_upper(const double* src, int ld, int bs, int j, double* zs) {
-  for (int i = 0; i <= j && i < bs; ++i) zs[i * 33 + j] = (i == j) ? 1.0 : 0.0;
   const double rd = (j < bs) ? 1.0 / src[j * ld + j] : 1.0;   // lane j: reciprocal of pivot j
-  for (int k = bs - 1; k >= 0; --k) {
-    const double rk = __shfl_sync(0xffffffffu, rd, k);
-    const double zk = (k <= j) ? zs[k * 33 + j] * rk : 0.0;
-    if (k <= j) zs[k * 33 + j] = zk;
-    const double* uk = src + k * ld;
-#pragma unroll 4
-    for (int i = 0; i < k; ++i)
-      if (k <= j) zs[i * 33 + j] -= uk[i] * zk;
+  for (int R0 = bs - 8; R0 >= 0; R0 -= 8) {
+    double acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+    for (int k = bs - 1; k >= R0 + 8; --k) {
+      const double zl = zs[k * 33 + j];
+      const double zk = (k > j) ? 0.0 : zl;
+      const double* uk = src + k * ld + R0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] -= uk[r] * zk;
+    }
+    double z[8];
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+      const int i = R0 + r;
+      double v = acc[r] + ((i == j) ? 1.0 : 0.0);
+#pragma unroll
+      for (int r2 = r + 1; r2 < 8; ++r2) v -= src[(R0 + r2) * ld + i] * z[r2];
+      const double ri = __shfl_sync(0xffffffffu, rd, i);
+      z[r] = (i > j) ? 0.0 : v * ri;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (R0 + r <= j) zs[(R0 + r) * 33 + j] = z[r];
   }
 }
 
@@ -477,6 +522,38 @@ __device__ __noinline__ void block_inverses() {
   }
 }
 
+// One ELL group of the level-parallel factorisation with a compile-time width W (entries per
+// target): NB targets per lane and step, all index loads first, then all operand reads, then
+// the arithmetic.  ep/tp point at this lane's first entry / target of the warp's block range.
+template <int W, int NB>
+__device__ __forceinline__ void glu_group(const uint32_t* __restrict__ ep, const uint16_t* __restrict__ tp,
+                                          int nb, double* V, int zp, uint32_t ZZ) {
+  for (int b0 = 0; b0 < nb; b0 += NB) {
+    uint32_t e[NB][W], t[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const bool on = b0 + u < nb;
+      t[u] = on ? (uint32_t)__ldcg(tp + (b0 + u) * 32) : (uint32_t)(zp + 1);
+#pragma unroll
+      for (int j = 0; j < W; ++j) e[u][j] = on ? __ldcg(ep + ((b0 + u) * W + j) * 32) : ZZ;
+    }
+    double lv[NB][W], uv[NB][W], tv[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      if (t[u] == 0xFFFFu) t[u] = (uint32_t)(zp + 1);     // idle lane: the trash slot
+      tv[u] = V[t[u]];
+#pragma unroll
+      for (int j = 0; j < W; ++j) { lv[u][j] = V[e[u][j] & 0xffffu]; uv[u][j] = V[e[u][j] >> 16]; }
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+#pragma unroll
+      for (int u = 0; u < NB; ++u) tv[u] -= lv[u][j] * uv[u][j];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) V[t[u]] = tv[u];
+  }
+}
+
 // P = I - hl0*J and its LU, level-parallel ("gather") formulation: see HostNet::LevelLU.
 // The whole factor V (storage order) is in shared memory.  Returns 0 ok / 1 zero pivot.
 __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned long long* ph) {
@@ -504,61 +581,162 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
   for (int a = tid; a < nt; a += NT) sm.Dt[a * ldt + a] += 1.0;
   __syncthreads();
   const long long t0b = clock64();
+  const uint32_t ZZ = (uint32_t)g.zpos | ((uint32_t)g.zpos << 16);
+  const int zp = g.zpos;
+  // index entries of the next level's pivot/multiplier phase are fetched one level ahead
+  uint32_t pe, m0, m1;
+  {
+    const int4 L0 = sm.lvl[0], L1 = sm.lvl[1];
+    pe = (L0.x + tid < L1.x) ? __ldg(g.piv + L0.x + tid) : ZZ;
+    m0 = (L0.y + tid < L1.y) ? __ldg(g.mul + L0.y + tid) : ZZ;
+    m1 = (L0.y + tid + NT < L1.y) ? __ldg(g.mul + L0.y + tid + NT) : ZZ;
+  }
   for (int lev = 0; lev < g.nlev; ++lev) {
-    const int4 L0 = g.lvl[lev], L1 = g.lvl[lev + 1];
     const long long tlev = clock64();
-    for (int q = L0.x + tid; q < L1.x; q += NT) {
+    const int4 L0 = sm.lvl[lev], L1 = sm.lvl[lev + 1];
+    // rank-1 level: the first target chunk pair and the first multiplier position of this warp
+    // are requested now and land during the multiplier phase
+    int4 A = make_int4(0, 0, 0, 0), B = make_int4(0, 0, 0, 0);
+    const uint2* tg = nullptr;
+    uint2 ca = make_uint2(0u, 0u), cb = ca;
+    uint32_t lpc = ZZ;
+    if (L0.w >= 0) {
+      A = sm.r1[2 * L0.w]; B = sm.r1[2 * L0.w + 1];   // {ua0, nua4, ub0, nub4}, {tgt_off, nr, nj4, 0}
+      tg = (const uint2*)g.r1tgt + B.x + l;
+      if (w < B.z && B.y > 0) {
+        ca = __ldcg(tg + w * 32);
+        cb = (w + NW < B.z) ? __ldcg(tg + (w + NW) * 32) : ca;
+        lpc = (l < B.y) ? __ldg(g.mul + L0.y + l) : ZZ;
+      }
+    }
+    // multipliers l(i,k) = a(i,k) / a(k,k); the pivots' reciprocals are kept for the solves
+    if (L0.x + tid < L1.x) {
+      const double d = V[pe & 0xffffu];
+      if (d == 0.0 || isnan(d)) *flag = 1;
+      sm.dinv[pe >> 16] = 1.0 / d;
+    }
+    {
+      const double a0 = V[m0 & 0xffffu], d0 = V[m0 >> 16], a1 = V[m1 & 0xffffu], d1 = V[m1 >> 16];
+      if (L0.y + tid < L1.y) V[m0 & 0xffffu] = a0 / d0;
+      if (L0.y + tid + NT < L1.y) V[m1 & 0xffffu] = a1 / d1;
+    }
+    for (int q = L0.x + NT + tid; q < L1.x; q += NT) {
       const uint32_t e = __ldg(g.piv + q);
       const double d = V[e & 0xffffu];
       if (d == 0.0 || isnan(d)) *flag = 1;
       sm.dinv[e >> 16] = 1.0 / d;
     }
-    __syncthreads();
-    for (int q = L0.y + tid; q < L1.y; q += NT) {
+    for (int q = L0.y + 2 * NT + tid; q < L1.y; q += NT) {
       const uint32_t e = __ldg(g.mul + q);
-      V[e & 0xffffu] *= sm.dinv[e >> 16];
+      V[e & 0xffffu] = V[e & 0xffffu] / V[e >> 16];
     }
     __syncthreads();
     long long tq = clock64();
     if (tid == 0) ph[PH_G_PIVMUL] += tq - tlev;
+    if (lev + 1 < g.nlev) {
+      const int4 L2 = sm.lvl[lev + 2];
+      pe = (L1.x + tid < L2.x) ? __ldg(g.piv + L1.x + tid) : ZZ;
+      m0 = (L1.y + tid < L2.y) ? __ldg(g.mul + L1.y + tid) : ZZ;
+      m1 = (L1.y + tid + NT < L2.y) ? __ldg(g.mul + L1.y + tid + NT) : ZZ;
+    }
+    // updates a(i,j) -= sum_k l(i,k) u(k,j)
+    if (L0.w >= 0) {
+      // single pivot k: outer product rows(k) x cols(k).  Lane = row of a 32-row chunk (its
+      // multiplier in a register), warp = every NW-th chunk of 4 columns, two chunks per step;
+      // the target positions of the next step are in flight while this one is applied
+      const int nr = B.y, nj4 = B.z;
+      int rc = 0, j4 = w;
+      bool have = (w < nj4) && nr > 0;
+      double lv = 0.0;
+      bool fresh = true;
+      while (have) {
+        if (fresh) { lv = (rc * 32 + l < nr) ? V[lpc & 0xffffu] : 0.0; fresh = false; }
+        int nrc = rc, nj = j4 + 2 * NW;
+        if (nj >= nj4) { nj = w; ++nrc; }
+        const bool hnext = nrc * 32 < nr;
+        uint2 na = ca, nb2 = cb;
+        uint32_t lpn = lpc;
+        if (hnext) {
+          const uint2* tp = tg + (size_t)nrc * nj4 * 32;
+          na = __ldcg(tp + nj * 32);
+          nb2 = (nj + NW < nj4) ? __ldcg(tp + (nj + NW) * 32) : na;
+          if (nrc != rc) lpn = (nrc * 32 + l < nr) ? __ldg(g.mul + L0.y + nrc * 32 + l) : ZZ;
+        }
+        const int j4b = j4 + NW;
+        const bool two = j4b < nj4;
+        const int ua = (j4 < A.y) ? A.x + 4 * j4 : A.z + 4 * (j4 - A.y);
+        const int ub = (j4b < A.y) ? A.x + 4 * j4b : A.z + 4 * (j4b - A.y);
+        const int t0 = ca.x & 0xffffu, t1 = ca.x >> 16, t2 = ca.y & 0xffffu, t3 = ca.y >> 16;
+        double u[4], tv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) u[c] = V[ua + c];
+        tv[0] = V[t0]; tv[1] = V[t1]; tv[2] = V[t2]; tv[3] = V[t3];
+        if (two) {
+          const int s0 = cb.x & 0xffffu, s1 = cb.x >> 16, s2 = cb.y & 0xffffu, s3 = cb.y >> 16;
+          double u2[4], sv[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) u2[c] = V[ub + c];
+          sv[0] = V[s0]; sv[1] = V[s1]; sv[2] = V[s2]; sv[3] = V[s3];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { tv[c] -= lv * u[c]; sv[c] -= lv * u2[c]; }
+          V[t0] = tv[0]; V[t1] = tv[1]; V[t2] = tv[2]; V[t3] = tv[3];
+          V[s0] = sv[0]; V[s1] = sv[1]; V[s2] = sv[2]; V[s3] = sv[3];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tv[c] -= lv * u[c];
+          V[t0] = tv[0]; V[t1] = tv[1]; V[t2] = tv[2]; V[t3] = tv[3];
+        }
+        fresh = nrc != rc;
+        ca = na; cb = nb2; lpc = lpn; rc = nrc; j4 = nj; have = hnext;
+      }
+      if (tid == 0) { const long long tn2 = clock64(); ph[PH_G_FLAT] += tn2 - tq; tq = tn2; }
+    }
+    int rot = 0;
     for (int gi = L0.z; gi < L1.z; ++gi) {
-      const int4 G = g.grp[gi];      // {width, nblk, ent_off, tgt_off}
-      if (G.x == 1) {
-        // one pair per target: a flat list, four independent items in flight per thread
-        const int cnt = G.y * 32;
-        const uint32_t* ep = g.ent + G.z;
-        const uint16_t* tp = g.tgt + G.w;
-        for (int q0 = tid; q0 < cnt; q0 += 4 * NT) {
-          uint32_t ev[4]; uint32_t tv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int q = q0 + u * NT;
-            ev[u] = (q < cnt) ? __ldcs(ep + q) : 0u;
-            tv[u] = (q < cnt) ? (uint32_t)__ldcs(tp + q) : 0xFFFFu;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (tv[u] != 0xFFFFu) V[tv[u]] -= V[ev[u] & 0xffffu] * V[ev[u] >> 16];
+      const int4 G = sm.grp[gi];     // {width, nblk, ent_off, tgt_off}
+      // contiguous block range of this warp; the warp that gets the remainder rotates from group
+      // to group so that runs of one-block groups spread over all warps
+      const int wr = (w + rot) & (NW - 1);
+      rot += G.y;
+      const int b_lo = (G.y * wr) / NW, nb = (G.y * (wr + 1)) / NW - b_lo;
+      const uint32_t* ep = g.ent + G.z + (size_t)b_lo * G.x * 32 + l;
+      const uint16_t* tp = g.tgt + G.w + b_lo * 32 + l;
+      if (G.x <= 8) {
+        switch (G.x) {     // uniform
+          case 1: glu_group<1, 8>(ep, tp, nb, V, zp, ZZ); break;
+          case 2: glu_group<2, 8>(ep, tp, nb, V, zp, ZZ); break;
+          case 3: glu_group<3, 4>(ep, tp, nb, V, zp, ZZ); break;
+          case 4: glu_group<4, 4>(ep, tp, nb, V, zp, ZZ); break;
+          case 5: glu_group<5, 2>(ep, tp, nb, V, zp, ZZ); break;
+          case 6: glu_group<6, 2>(ep, tp, nb, V, zp, ZZ); break;
+          case 7: glu_group<7, 2>(ep, tp, nb, V, zp, ZZ); break;
+          default: glu_group<8, 2>(ep, tp, nb, V, zp, ZZ); break;
         }
       } else {
-        for (int b = w; b < G.y; b += NW) {
-          const uint32_t* ep = g.ent + G.z + (size_t)b * G.x * 32 + l;
-          const uint32_t t = __ldcs(g.tgt + G.w + b * 32 + l);
-          double a0 = 0.0, a1 = 0.0;
-          for (int j0 = 0; j0 < G.x; j0 += 8) {
-            uint32_t ev[8];
+        for (int b = 0; b < nb; ++b) {
+          const uint32_t* eb = ep + (size_t)b * G.x * 32;
+          const uint32_t t = (uint32_t)__ldcg(tp + b * 32);
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          uint32_t e[16], en[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ev[j] = (j0 + j < G.x) ? __ldcs(ep + (j0 + j) * 32) : 0u;
+          for (int j = 0; j < 16; ++j) e[j] = (j < G.x) ? __ldcg(eb + j * 32) : ZZ;
+          for (int j0 = 0; j0 < G.x; j0 += 16) {
+            if (j0 + 16 < G.x) {
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              if (j0 + j < G.x) a0 += V[ev[j] & 0xffffu] * V[ev[j] >> 16];
-              if (j0 + j + 1 < G.x) a1 += V[ev[j + 1] & 0xffffu] * V[ev[j + 1] >> 16];
+              for (int j = 0; j < 16; ++j) en[j] = (j0 + 16 + j < G.x) ? __ldcg(eb + (j0 + 16 + j) * 32) : ZZ;
             }
+            double lv[16], uv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { lv[j] = V[e[j] & 0xffffu]; uv[j] = V[e[j] >> 16]; }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j & 3] += lv[j] * uv[j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) e[j] = en[j];
           }
-          if (t != 0xFFFFu) V[t] -= a0 + a1;
+          if (t != 0xFFFFu) V[t] -= (acc[0] + acc[1]) + (acc[2] + acc[3]);
         }
       }
-      if (tid == 0) { const long long tn = clock64(); ph[G.x == 1 ? PH_G_FLAT : (G.x <= 8 ? PH_G_NARROW : PH_G_WIDE)] += tn - tq; tq = tn; }
+      if (tid == 0) { const long long tn2 = clock64(); ph[G.x == 1 ? PH_G_FLAT : (G.x <= 8 ? PH_G_NARROW : PH_G_WIDE)] += tn2 - tq; tq = tn2; }
     }
     __syncthreads();
     if (tid == 0) ph[PH_G_PIVMUL] += clock64() - tq;
@@ -568,7 +746,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
   for (int q = tid; q < net.n_ub; q += NT) ws.ubE[__ldg(net.ub_ellpos + q)] = V[net.o_ub + q];
   for (int q = tid; q < net.n_lc; q += NT) ws.lcE[__ldg(net.lc_ellpos + q)] = V[net.o_lc + q];
   __syncthreads();   // X (= the U_B/L_C part of V) is scratch from here on
-  if (tid == 0) ph[PH_G_COPY] += clock64() - t1;
+  if (tid == 0) { ph[PH_G_COPY] += clock64() - t1; ph[PH_IO] += t1 - t0b; }
   const long long t2 = clock64();
   // ---- tables of the staged solves and dense copies of the S diagonal blocks -> upper part of X
   {
@@ -887,7 +1065,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
   ell_fetch(net.lcE, ws.lcE, R);           // lands while the head sweep runs
   for (int i = tid; i < n; i += NT) sm.xb[i] = sm.y[__ldg(net.perm + i)];
   __syncthreads();
-  for (int st = 0; st < net.ss.nf; ++st) head_stage(net.ss.st[st], sm, ent, rp, rows, tmp, false);
+  for (int st = 0; st < net.ss.nf; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, false);
   const long long t1 = clock64();
   // ---- tail right-hand side: x_T -= L_C x_H
   ell_apply(net.lcE, R, sm.xb, sm.xb + nh, part);
@@ -935,7 +1113,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
   // ---- head right-hand side: x_H -= U_B x_T
   ell_apply(net.ubE, R, sm.xb + nh, sm.xb, part);
   const long long t2 = clock64();
-  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(net.ss.st[st], sm, ent, rp, rows, tmp, true);
+  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, true);
   for (int i = tid; i < n; i += NT) sm.y[__ldg(net.perm + i)] = sm.xb[i];
   __syncthreads();
   if (tid == 0) {
@@ -1120,6 +1298,8 @@ integrate_kernel(const BatchArgs args) {
     double* V = smem_raw + lay.voff;      // the factor in storage order: [hh | U_B | L_C | tail]
     sm.hh = V; sm.X = V + net.o_ub; sm.Dt = V + net.o_tl;
     sm.hhcol = nullptr; sm.fthin = nullptr; sm.bthin = nullptr; sm.flptr = nullptr; sm.suptr = nullptr;
+    int4* dsc = (int4*)(smem_raw + net.glu.doff);
+    for (int q = tid; q < net.glu.ndesc; q += NT) dsc[q] = net.glu.desc[q];
   } else {
     double* p = smem_raw;
     sm.y = p; p += n; sm.savf = p; p += n; sm.xb = sm.savf; sm.dinv = p; p += net.nh;
@@ -1140,8 +1320,7 @@ integrate_kernel(const BatchArgs args) {
     sm.fthin = ft; sm.bthin = bt; sm.flptr = fl; sm.suptr = su; sm.hhcol = hc;
     sm.X = p;
   }
-  double* fx = sm.X;                 // flux / dflux [R]
-  double* px = sm.X + R;             // gather partials
+  const int x_off = (int)(sm.X - smem_raw);   // scratch region: fluxes [R] | gather partials
   const double* ks = ws.ksave;
   unsigned long long* const ph = s_ph;
   if (tid < PH_COUNT) s_ph[tid] = 0;
@@ -1259,7 +1438,7 @@ integrate_kernel(const BatchArgs args) {
             case D_BLOCKC: {
               s.TN = t; s.NST = 0; s.H = 1.0;
               FORE { yh[e][0] = sm.y[i]; yh[e][2] = 0.0; yh[e][3] = 0.0; yh[e][4] = 0.0; yh[e][5] = 0.0; }
-              { long long ta = clock64(); eval_f(ks, fx, px, sm.y, sm.savf, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
+              { long long ta = clock64(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
               FORE yh[e][1] = sm.savf[i];
               s.NFE = 1;
               bool bad = false;
@@ -1404,7 +1583,7 @@ integrate_kernel(const BatchArgs args) {
                     M = 0;
                     FORE sm.y[i] = yh[e][0];
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); eval_f(ks, fx, px, sm.y, sm.savf, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     if (s.IPUP <= 0) { pc = L250; break; }
@@ -1437,7 +1616,7 @@ integrate_kernel(const BatchArgs args) {
                         s.JCUR = 1; s.NJE = s.NJE + 1; s.NSLJ = s.NST; s.IPLOST = 0; s.CONMIN = fabs(CON);
                         if (tid == 0) ph[PH_VEC] += clock64() - tv;
                         long long ta = clock64();
-                        eval_jac(ks, fx, px, sm.y, ws.J, DS);
+                        eval_jac(ks, x_off, ws.J, DS);
                         if (tid == 0) ph[PH_JAC] += clock64() - ta;
                         tv = clock64();
                         s.wiped = 0;
@@ -1482,7 +1661,7 @@ integrate_kernel(const BatchArgs args) {
                     if (M >= 2 && DEL > 2.0 * DELP) { pc = L410; break; }
                     DELP = DEL;
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); __syncthreads(); eval_f(ks, fx, px, sm.y, sm.savf, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); __syncthreads(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     pc = L270;
@@ -1599,7 +1778,7 @@ integrate_kernel(const BatchArgs args) {
                     __syncthreads();
                     FORE sm.y[i] = yh[e][0];
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); __syncthreads(); eval_f(ks, fx, px, sm.y, sm.savf, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); __syncthreads(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     FORE yh[e][1] = s.H * sm.savf[i];
@@ -1775,13 +1954,14 @@ size_t integrate_smem_bytes(DevNet& net) {
     if ((size_t)(NW / 2) * 33 * 32 > x_f) x_f = (size_t)(NW / 2) * 33 * 32;
     x_f = (x_f + 1) & ~(size_t)1;
     const size_t big = (227 * 1024 - 1024) / 8;
-    const size_t voff = (2 * n + net.nh + 32 + 2 * NW + 1) & ~(size_t)1;
+    const size_t doff = (2 * n + net.nh + 32 + 2 * NW + 1) & ~(size_t)1;   // int4 descriptors (16-byte aligned)
+    const size_t voff = doff + 2 * (size_t)net.glu.ndesc;
     const size_t xg = (size_t)(net.o_tl - net.o_ub);
     const size_t sinv = x_f, tab = sinv + (size_t)net.ss.nblkS * 33 * 32;
     const size_t xend = tab + ((size_t)net.ss.blob_words + 1) / 2;
     if (voff + net.nstore + 2 <= big && xend <= xg && net.o_ub == net.n_hh &&
         net.ubE.nblk <= 2 * NW && net.lcE.nblk <= 2 * NW) {
-      net.glu.voff = (int)voff; net.ss.xlow = (int)x_f; net.ss.sinv = (int)sinv; net.ss.tab = (int)tab;
+      net.glu.voff = (int)voff; net.glu.doff = (int)doff; net.ss.xlow = (int)x_f; net.ss.sinv = (int)sinv; net.ss.tab = (int)tab;
     } else net.glu.on = 0;
   }
   return make_layout(net).total * sizeof(double);
