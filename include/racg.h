@@ -159,6 +159,14 @@ int racg_solve_batch_dev(racg_handle* h, int ncell, const double* cellpar, const
                          const racg_solve_params* sp, double* y_final, double* t_final,
                          double* touts, double* record, int* nrec_real, int* istate,
                          int* quality, double* stats, void* stream);
+/* diagnostics: f(y) and the Jacobian as the integrator's own in-kernel routines compute them
+ * (not the stand-alone K2/K3 kernels).  y(ncell,NEQ) -> f(ncell,NEQ) [slot NEQ undefined],
+ * jstore(ncell,nstore) in the library's LU storage order; csc_to_store(NNZ) maps the slots of
+ * racg_network_pattern to that order (-1: structurally zero for evolT=.false.).  With
+ * ncell <= 0 only *nstore and csc_to_store are filled.  con != 0: f receives instead the solution
+ * x of (I + con*J) x = f(y) from the integrator's own factorisation and solve (con = -h*el0). */
+int racg_debug_fjac(racg_handle* h, int ncell, const double* cellpar, const double* y, double* f,
+                    double* jstore, int* csc_to_store, int* nstore, double con);
 /* number of kernel launches issued through this handle so far */
 long racg_launch_count(const racg_handle* h);
 /* per-phase SM-cycle counters of the last racg_solve_batch* call, summed over CTAs:

@@ -1,3 +1,6 @@
+#include <algorithm>
+#include <vector>
+#include <cstdlib>
 // raco_chem.cpp -- ORACLE (test infrastructure only, see raco.h): rate coefficients,
 // RHS and Jacobian for one cell, restating src/chemistry.f90:591-966,1007-1086,
 // 1532-1590 and the fixed-T branches of src/disk.f90:4569-4659, 4746-4903.
@@ -251,7 +254,12 @@ static inline bool flux(const Net& n, const raco_cfg& c, const double* p, const 
 void ode_f(const Net& n, const raco_cfg& c, const double* p, const double* rates, const double* y,
            double* ydot) {
   for (int i = 0; i < n.NEQ; ++i) ydot[i] = 0.0;
-  for (int i = 0; i < n.R; ++i) {
+  static const int fsum_rev = getenv("ORACLE_FSUM_REVERSE") ? 1 : 0;   // diagnostics: summation order
+  static const int fsum_gpu = getenv("ORACLE_FSUM_GPU") ? atoi(getenv("ORACLE_FSUM_GPU")) : 0;
+  std::vector<std::vector<double>> terms;
+  if (fsum_gpu) terms.resize(n.NEQ);
+  for (int ii = 0; ii < n.R; ++ii) {
+    const int i = fsum_rev ? n.R - 1 - ii : ii;
     double rtmp;
     if (n.itype[i] == 63 && n.first_is_gH[i] && c.H2_form_use_moeq) {
       int r1 = n.reac[3 * i];
@@ -263,8 +271,31 @@ void ode_f(const Net& n, const raco_cfg& c, const double* p, const double* rates
     } else if (!flux(n, c, p, rates, y, i, rtmp)) {
       continue;
     }
+    if (fsum_gpu) {
+      // diagnostics: collect the terms per species (net stoichiometry per reaction, as the GPU does)
+      int sp[7], cf[7], m = 0;
+      auto add = [&](int s_, int c_) { for (int q = 0; q < m; ++q) if (sp[q] == s_) { cf[q] += c_; return; } sp[m] = s_; cf[m] = c_; ++m; };
+      for (int j = 0; j < n.n_reac[i]; ++j) add(n.reac[3 * i + j] - 1, -1);
+      for (int j = 0; j < n.n_prod[i]; ++j) add(n.prod[4 * i + j] - 1, +1);
+      for (int q = 0; q < m; ++q) if (cf[q] != 0) terms[sp[q]].push_back((double)cf[q] * rtmp);
+      continue;
+    }
     for (int j = 0; j < n.n_reac[i]; ++j) ydot[n.reac[3 * i + j] - 1] -= rtmp;
     for (int j = 0; j < n.n_prod[i]; ++j) ydot[n.prod[4 * i + j] - 1] += rtmp;
+  }
+  if (fsum_gpu) {
+    for (int s_ = 0; s_ < n.NEQ; ++s_) {
+      const std::vector<double>& t = terms[s_];
+      double tot = 0.0;
+      for (size_t c0 = 0; c0 < t.size(); c0 += 32) {
+        double acc[4] = {0, 0, 0, 0};
+        const size_t c1 = std::min(t.size(), c0 + 32);
+        if (fsum_gpu == 1) { for (size_t q = c0; q < c1; ++q) acc[(q - c0) & 3] += t[q]; }
+        else { for (size_t q = c0; q < c1; ++q) acc[0] += t[q]; }
+        tot += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      }
+      ydot[s_] = tot;
+    }
   }
   ydot[n.NEQ - 1] = 0.0;
 }

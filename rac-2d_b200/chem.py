@@ -276,6 +276,23 @@ class ChemSolver:
                                           v(d_touts), v(d_record), v(d_nrec), v(d_ist), v(d_q), v(d_stats),
                                           v(stream)))
 
+    def debug_fjac(self, cellpar, y, con=0.0):
+        """f and J (as a CSC value array in the slot order of pattern()) from the integrator's
+        in-kernel routines"""
+        cellpar = _f(cellpar); y = _f(y)
+        ncell = cellpar.shape[0]
+        nstore = C.c_int(0)
+        c2s = np.zeros(self.NNZ, dtype=np.int32)
+        _check(lib().racg_debug_fjac(self.h, 0, None, None, None, None, _p(c2s), C.byref(nstore), C.c_double(0.0)))
+        par_t = np.ascontiguousarray(cellpar.T); y_t = np.ascontiguousarray(y.T)
+        f_t = np.zeros((self.NEQ, ncell)); j_t = np.zeros((nstore.value, ncell))
+        _check(lib().racg_debug_fjac(self.h, ncell, _p(par_t), _p(y_t), _p(f_t), _p(j_t), _p(c2s), C.byref(nstore),
+                                     C.c_double(con)))
+        pd = np.zeros((ncell, self.NNZ))
+        m = c2s >= 0
+        pd[:, m] = j_t[c2s[m], :].T
+        return f_t.T.copy(), pd
+
     def launch_count(self):
         return int(lib().racg_launch_count(self.h))
 

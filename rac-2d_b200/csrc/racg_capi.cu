@@ -40,6 +40,8 @@ struct racg_handle {
   int* d_queue = nullptr;
   unsigned long long* d_phase = nullptr;
   long launches = 0;
+  double* dbg_J = nullptr;   // set only inside racg_debug_fjac
+  double dbg_con = 0.0;
 };
 
 template <typename T>
@@ -211,6 +213,7 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
     dn.glu.on = 0;
     if (g.nlev > 0 && ss.nent > 0 && !getenv("RACG_NO_GLU")) {
       dn.glu.on = 1; dn.glu.nlev = g.nlev; dn.glu.zpos = g.zpos;
+      dn.glu.subst = getenv("RACG_SUBST") ? atoi(getenv("RACG_SUBST")) : 0;
       UP(g.piv, glu.piv); UP(g.mul, glu.mul); UP(g.ent, glu.ent); UP(g.tgt, glu.tgt);
       std::vector<int> desc(g.lvl);
       desc.insert(desc.end(), g.grp.begin(), g.grp.end());
@@ -362,6 +365,7 @@ int racg_solve_batch_dev(racg_handle* h, int ncell, const double* cellpar, const
   a.dt_first = dt_first; a.sp = *sp; a.y_final = y_final; a.t_final = t_final; a.touts = touts; a.record = record;
   a.nrec_real = nrec_real; a.istate = istate; a.quality = quality; a.stats = stats;
   a.queue = h->d_queue; a.ws = h->d_ws; a.ws_stride = h->ws_stride; a.phase = h->d_phase;
+  a.dbg_J = h->dbg_J; a.dbg_con = h->dbg_con;
   CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), st));
   CK(cudaMemsetAsync(h->d_phase, 0, RACG_NPHASE * sizeof(unsigned long long), st));
   int nblocks = ncell < h->nblocks ? ncell : h->nblocks;
@@ -450,6 +454,29 @@ int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const dou
   CK(cudaMemcpy(stats, d_st, sizeof(double) * RACG_NSTAT * nc, cudaMemcpyDeviceToHost));
   if (touts) CK(cudaMemcpy(touts, d_touts, sizeof(double) * nrec * nc, cudaMemcpyDeviceToHost));
   if (record) CK(cudaMemcpy(record, d_rec, sizeof(double) * nrec * NEQ * nc, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int racg_debug_fjac(racg_handle* h, int ncell, const double* cellpar, const double* y, double* f,
+                    double* jstore, int* csc_to_store, int* nstore, double con) {
+  int rc = need_gpu(h); if (rc) return rc;
+  const HostNet& hn = h->hn;
+  if (nstore) *nstore = hn.nstore;
+  if (csc_to_store) memcpy(csc_to_store, hn.csc_to_store.data(), sizeof(int) * hn.NNZ);
+  if (!cellpar || !y || !f || !jstore || ncell <= 0) return 0;
+  const size_t nc = ncell, NEQ = hn.NEQ;
+  DevBuf buf;
+  ALLOC(double, d_J, (size_t)hn.nstore * nc);
+  std::vector<double> t0(nc, 0.0), tm(nc, 1.0), dt(nc, 1e-8), tf(nc), st((size_t)RACG_NSTAT * nc);
+  std::vector<int> ii(3 * nc);
+  racg_solve_params sp; sp.ratio_tstep = 1.1; sp.mxstep_per_interval = 10; sp.steps_reset_solver = 50;
+  sp.nrec_max = 2; sp.tol_policy_j = 1; sp.RTOL = 1e-4; sp.ATOL = 1e-30;
+  h->dbg_J = d_J; h->dbg_con = con;
+  rc = racg_solve_batch(h, ncell, cellpar, y, nullptr, nullptr, t0.data(), tm.data(), dt.data(), &sp, f, tf.data(),
+                        nullptr, nullptr, ii.data(), ii.data() + nc, ii.data() + 2 * nc, st.data());
+  h->dbg_J = nullptr; h->dbg_con = 0.0;
+  if (rc) return rc;
+  CK(cudaMemcpy(jstore, d_J, sizeof(double) * hn.nstore * nc, cudaMemcpyDeviceToHost));
   return 0;
 }
 

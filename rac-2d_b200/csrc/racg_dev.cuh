@@ -36,6 +36,7 @@ struct EllDev {
 // constant-cache miss.
 struct GluDev {
   int on, nlev, zpos, voff;
+  int subst;                  // 1: triangular substitution inside the diagonal blocks instead of explicit inverses
   int ngrp, ndesc, doff;      // descriptor block: [lvl (nlev+1) | grp (ngrp) | stages (nst) | rank-1 pairs]; doff = offset in smem (doubles)
   const uint32_t* piv; const uint32_t* mul; const uint32_t* ent; const uint16_t* tgt;
   const uint16_t* r1tgt;      // rank-1 levels: 4 target positions per (row chunk, column chunk, lane)
@@ -109,6 +110,11 @@ struct BatchArgs {
   double* ws;                // per-CTA workspace
   size_t ws_stride;          // doubles per CTA
   unsigned long long* phase; // [RACG_NPHASE] cycle counters
+  // diagnostics (racg_debug_fjac): when set, the kernel evaluates f and J at y0 with its own
+  // in-kernel routines, writes f to y_final and J (storage order) to dbg_J [nstore][ncell], and
+  // skips the integration
+  double* dbg_J;
+  double dbg_con;            // != 0: additionally factor P = I + dbg_con*J and return P^-1 f in y_final
 };
 
 // stand-alone K3 column-group schedule (racg_batch.cu)

@@ -161,7 +161,11 @@ __device__ __forceinline__ void run_gather(const GatherDev& g, const double* src
     uint32_t ev[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) ev[j] = (j < width) ? __ldcg(e + j * 32) : (4u << 24);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // ONE accumulator, terms in reaction order as the reference's loop adds them: forward and
+    // reverse reactions sit next to each other in the network file and cancel term by term.
+    // Interleaved partial sums lose that cancellation and the extra round-off in f makes the
+    // corrector of very stiff cells fail (3x more steps were measured).
+    double a = 0.0;
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += 8) {
       if (j0 < width) {
@@ -171,11 +175,10 @@ __device__ __forceinline__ void run_gather(const GatherDev& g, const double* src
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = (int)(ev[j0 + j] >> 24) - 4;
-          acc[j & 3] += (c != 0) ? (double)c * sv[j] : 0.0;
+          a += (c != 0) ? (double)c * sv[j] : 0.0;
         }
       }
     }
-    const double a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     const int t = __ldg(g.sub_target + b * 32 + l);
     if (t >= 0) {
       if (GLOBAL_OUT && g.sub_add && g.sub_add[b * 32 + l]) out[t] += a; else out[t] = a;
@@ -770,7 +773,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
     case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
   }
   const long long t2b = clock64();
-  block_inverses();
+  if (!net.glu.subst) block_inverses();
   const int res = *flag;
   __syncthreads();
   if (tid == 0) {
@@ -969,6 +972,23 @@ __device__ __forceinline__ double block_apply(const double* T, int ld, int bs, b
   return upper ? mv : mv + tmp[r < 32 ? r : 0];
 }
 
+// in-block triangular substitution by one warp (lane r owns row r); T column-major, ld
+__device__ __forceinline__ double block_subst(const double* T, int ld, int bs, bool upper, double v, int r) {
+  if (!upper) {
+    for (int c = 0; c < bs; ++c) {
+      const double xc = __shfl_sync(0xffffffffu, v, c);
+      if (r > c && r < bs) v -= T[c * ld + r] * xc;
+    }
+  } else {
+    for (int c = bs - 1; c >= 0; --c) {
+      if (r == c) v = v / T[c * ld + c];
+      const double xc = __shfl_sync(0xffffffffu, v, c);
+      if (r < c) v -= T[c * ld + r] * xc;
+    }
+  }
+  return v;
+}
+
 __device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const uint32_t* ent, const uint16_t* rp,
                                            const uint16_t* rows, double* tmp, bool upper) {
   const DevNet& net = c_net;
@@ -999,6 +1019,14 @@ __device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const ui
   }
   if (sub == 0) tmp[r] = (r < nrows) ? sm.xb[row] - acc : 0.0;
   __syncthreads();
+  if (net.glu.subst) {
+    if (tid < 32) {
+      const double xv = block_subst(sm.X + net.ss.sinv + blk * (33 * 32), 33, 32, upper, tmp[tid], tid);
+      if (tid < nrows) sm.xb[rows[S.z + tid]] = xv;
+    }
+    __syncthreads();
+    return;
+  }
   const double xv = block_apply(sm.X + net.ss.sinv + blk * (33 * 32), 33, 32, upper, tmp, r, sub);
   if (sub == 0 && r < nrows) sm.xb[row] = xv;
   __syncthreads();
@@ -1088,8 +1116,12 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
       const double acc = group_sum(a0 + a1, 8);
       if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
       __syncthreads();
-      const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, false, tmp, r, sg);
-      if (sg == 0 && r < bs) xt[row] = xv;
+      if (net.glu.subst) {
+        if (tid < 32) { const double xv = block_subst(sm.Dt + (o * ldt + o), ldt, bs, false, tmp[tid], tid); if (tid < bs) xt[o + tid] = xv; }
+      } else {
+        const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, false, tmp, r, sg);
+        if (sg == 0 && r < bs) xt[row] = xv;
+      }
       __syncthreads();
     }
     for (int m = nbT - 1; m >= 0; --m) {     // backward, upper; diagonal blocks hold U^-1
@@ -1104,8 +1136,12 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
       const double acc = group_sum(a0 + a1, 8);
       if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
       __syncthreads();
-      const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, true, tmp, r, sg);
-      if (sg == 0 && r < bs) xt[row] = xv;
+      if (net.glu.subst) {
+        if (tid < 32) { const double xv = block_subst(sm.Dt + (o * ldt + o), ldt, bs, true, tmp[tid], tid); if (tid < bs) xt[o + tid] = xv; }
+      } else {
+        const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, true, tmp, r, sg);
+        if (sg == 0 && r < bs) xt[row] = xv;
+      }
       __syncthreads();
     }
   }
@@ -1383,6 +1419,24 @@ integrate_kernel(const BatchArgs args) {
       __syncthreads();
     }
     if (tid == 0) { long long t = clock64(); ph[PH_RATES] += t - tc; }
+    if (args.dbg_J) {   // diagnostics: in-kernel f and J at y0
+      eval_f(ks, x_off, DS, ph);
+      for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = sm.savf[i];
+      for (int q = tid; q < net.nstore; q += NT) ws.J[q] = 0.0;
+      __syncthreads();
+      eval_jac(ks, x_off, ws.J, DS);
+      for (int q = tid; q < net.nstore; q += NT) args.dbg_J[(size_t)q * ncell + cell] = ws.J[q];
+      __syncthreads();
+      if (args.dbg_con != 0.0) {
+        const int fl = GLU ? factor_glu(ws, args.dbg_con, &s_flag, ph) : factor<false>(ws, sm, lay, args.dbg_con, &s_flag, ph);
+        for (int i = tid; i < n; i += NT) sm.y[i] = sm.savf[i];
+        __syncthreads();
+        if (GLU) solve_glu(ws, ph); else solve(ws, sm, false, 1.0);
+        for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = fl ? nan("") : sm.y[i];
+        __syncthreads();
+      }
+      continue;
+    }
 
     // ---- chem_evol_solve (src/chemistry.f90:391-588)
     const double t_max = args.tmax[cell], t_start = args.t0[cell];
