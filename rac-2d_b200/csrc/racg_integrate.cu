@@ -559,7 +559,7 @@ __device__ __forceinline__ void glu_group(const uint32_t* __restrict__ ep, const
 
 // P = I - hl0*J and its LU, level-parallel ("gather") formulation: see HostNet::LevelLU.
 // The whole factor V (storage order) is in shared memory.  Returns 0 ok / 1 zero pivot.
-__device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned long long* ph) {
+__device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned long long* ph, int subst) {
   const GSm sm = glu_smem();
   const DevNet& net = c_net;
   const GluDev& g = net.glu;
@@ -773,7 +773,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
     case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
   }
   const long long t2b = clock64();
-  if (!net.glu.subst) block_inverses();
+  if (!subst) block_inverses();
   const int res = *flag;
   __syncthreads();
   if (tid == 0) {
@@ -980,8 +980,9 @@ __device__ __forceinline__ double block_subst(const double* T, int ld, int bs, b
       if (r > c && r < bs) v -= T[c * ld + r] * xc;
     }
   } else {
+    const double rd = (r < bs) ? 1.0 / T[r * ld + r] : 1.0;
     for (int c = bs - 1; c >= 0; --c) {
-      if (r == c) v = v / T[c * ld + c];
+      if (r == c) v = v * rd;
       const double xc = __shfl_sync(0xffffffffu, v, c);
       if (r < c) v -= T[c * ld + r] * xc;
     }
@@ -990,7 +991,7 @@ __device__ __forceinline__ double block_subst(const double* T, int ld, int bs, b
 }
 
 __device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const uint32_t* ent, const uint16_t* rp,
-                                           const uint16_t* rows, double* tmp, bool upper) {
+                                           const uint16_t* rows, double* tmp, bool upper, int subst) {
   const DevNet& net = c_net;
   const int tid = threadIdx.x;
   const int kind = S.x & 255, lg = (S.x >> 8) & 255, lpr = 1 << lg, nrows = S.y & 0xffff, blk = S.y >> 16;
@@ -1019,7 +1020,7 @@ __device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const ui
   }
   if (sub == 0) tmp[r] = (r < nrows) ? sm.xb[row] - acc : 0.0;
   __syncthreads();
-  if (net.glu.subst) {
+  if (subst) {
     if (tid < 32) {
       const double xv = block_subst(sm.X + net.ss.sinv + blk * (33 * 32), 33, 32, upper, tmp[tid], tid);
       if (tid < nrows) sm.xb[rows[S.z + tid]] = xv;
@@ -1078,7 +1079,7 @@ __device__ __forceinline__ void ell_apply(const EllDev& e, const EllRegs& R, con
   __syncthreads();
 }
 
-__device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
+__device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst) {
   const DevNet& net = c_net;
   const GSm sm = glu_smem();
   const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
@@ -1093,7 +1094,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
   ell_fetch(net.lcE, ws.lcE, R);           // lands while the head sweep runs
   for (int i = tid; i < n; i += NT) sm.xb[i] = sm.y[__ldg(net.perm + i)];
   __syncthreads();
-  for (int st = 0; st < net.ss.nf; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, false);
+  for (int st = 0; st < net.ss.nf; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, false, subst);
   const long long t1 = clock64();
   // ---- tail right-hand side: x_T -= L_C x_H
   ell_apply(net.lcE, R, sm.xb, sm.xb + nh, part);
@@ -1116,7 +1117,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
       const double acc = group_sum(a0 + a1, 8);
       if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
       __syncthreads();
-      if (net.glu.subst) {
+      if (subst) {
         if (tid < 32) { const double xv = block_subst(sm.Dt + (o * ldt + o), ldt, bs, false, tmp[tid], tid); if (tid < bs) xt[o + tid] = xv; }
       } else {
         const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, false, tmp, r, sg);
@@ -1136,7 +1137,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
       const double acc = group_sum(a0 + a1, 8);
       if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
       __syncthreads();
-      if (net.glu.subst) {
+      if (subst) {
         if (tid < 32) { const double xv = block_subst(sm.Dt + (o * ldt + o), ldt, bs, true, tmp[tid], tid); if (tid < bs) xt[o + tid] = xv; }
       } else {
         const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, true, tmp, r, sg);
@@ -1149,7 +1150,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
   // ---- head right-hand side: x_H -= U_B x_T
   ell_apply(net.ubE, R, sm.xb + nh, sm.xb, part);
   const long long t2 = clock64();
-  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, true);
+  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, true, subst);
   for (int i = tid; i < n; i += NT) sm.y[__ldg(net.perm + i)] = sm.xb[i];
   __syncthreads();
   if (tid == 0) {
@@ -1428,10 +1429,10 @@ integrate_kernel(const BatchArgs args) {
       for (int q = tid; q < net.nstore; q += NT) args.dbg_J[(size_t)q * ncell + cell] = ws.J[q];
       __syncthreads();
       if (args.dbg_con != 0.0) {
-        const int fl = GLU ? factor_glu(ws, args.dbg_con, &s_flag, ph) : factor<false>(ws, sm, lay, args.dbg_con, &s_flag, ph);
+        const int fl = GLU ? factor_glu(ws, args.dbg_con, &s_flag, ph, net.glu.subst) : factor<false>(ws, sm, lay, args.dbg_con, &s_flag, ph);
         for (int i = tid; i < n; i += NT) sm.y[i] = sm.savf[i];
         __syncthreads();
-        if (GLU) solve_glu(ws, ph); else solve(ws, sm, false, 1.0);
+        if (GLU) solve_glu(ws, ph, net.glu.subst); else solve(ws, sm, false, 1.0);
         for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = fl ? nan("") : sm.y[i];
         __syncthreads();
       }
@@ -1447,6 +1448,7 @@ integrate_kernel(const BatchArgs args) {
     double t = t_start, t_step = args.dt_first[cell], tout = t + t_step;
     int NERR = 0, nerr_c = 0, quality = 0, ISTATE = 1, n_record_real = 1;
     long long aNST = 0, aNFE = 0, aNJE = 0, aNLU = 0, nrestart = 0;
+    const int subst = net.glu.subst;   // diagnostics: substitution instead of inverse blocks (RACG_SUBST=1)
     Lsodes s;
     s.NST = s.NFE = s.NJE = s.NLU = s.NQU = 0; s.HU = 0.0; s.INIT = 0; s.IMXER = 0;
     s.n_solve = s.n_cfail = s.n_efail = 0; s.wiped = 0; s.pw = 0.0;
@@ -1681,7 +1683,7 @@ integrate_kernel(const BatchArgs args) {
                         flag = (s.pw == 0.0 || isnan(s.pw)) ? 1 : 0;
                       } else {
                         if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                        flag = GLU ? factor_glu(ws, CON, &s_flag, ph) : factor<false>(ws, sm, lay, CON, &s_flag, ph);
+                        flag = GLU ? factor_glu(ws, CON, &s_flag, ph, subst) : factor<false>(ws, sm, lay, CON, &s_flag, ph);
                         tv = clock64();
                       }
                       s.CON0 = CON;
@@ -1700,7 +1702,7 @@ integrate_kernel(const BatchArgs args) {
                     __syncthreads();
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
                     { long long ta = clock64(); if (s.wiped) { for (int i = tid; i < n; i += NT) sm.y[i] = sm.y[i] / s.pw; __syncthreads(); }
-                      else if (GLU) solve_glu(ws, ph);
+                      else if (GLU) solve_glu(ws, ph, subst);
                       else solve(ws, sm, false, s.pw);
                       if (tid == 0) ph[PH_SOLVE] += clock64() - ta; }
                     tv = clock64();

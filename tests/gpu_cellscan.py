@@ -10,7 +10,7 @@ sol = net.create_solver()
 y0s = net.chem_load_initial_abundances(os.path.join(inp, "initial_condition_Garrod08_mod_waterice.dat"))
 c = int(sys.argv[1])
 par1 = rb.synth.cell_params(1, first_cell=c)
-tm = np.array([1e3, 2e3, 4e3, 7e3, 1e4, 2e4, 4e4, 7e4, 1e5, 2e5, 5e5, 1e6])
+tm = np.array([1e2, 1e4, 1e5, 1e6])
 par = np.repeat(par1, len(tm), axis=0)
 y0 = rb.synth.initial_state(y0s, par, net.index("Grain0"))
 res = sol.chem_evol_solve(par, y0, t_max=tm, want_touts=False)

@@ -7,7 +7,8 @@ net = rb.ChemNetwork(os.path.join(inp, "rate06_dipole_reformated_again_withgrain
 sol = net.create_solver()
 y0s = net.chem_load_initial_abundances(os.path.join(inp, "initial_condition_Garrod08_mod_waterice.dat"))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2368
-par = rb.synth.cell_params(n)
+first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+par = rb.synth.cell_params(n, first_cell=first)
 y0 = rb.synth.initial_state(y0s, par, net.index("Grain0"))
 res = sol.chem_evol_solve(par, y0, want_touts=False)
 st = res["stats"]
