@@ -3,6 +3,7 @@
 // launches sm_100a kernels or fails with RACG_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@ namespace racg {
 size_t integrate_smem_bytes(DevNet& net);
 size_t integrate_ws_doubles(const DevNet& net);
 cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nblocks, size_t smem, cudaStream_t stream);
+void launch_cost(int ncell, const double* stats, float* cost, cudaStream_t st);
 // racg_batch.cu
 cudaError_t launch_rates(const DevNet& net, int ncell, const double* cellpar, double* rates, cudaStream_t st);
 cudaError_t launch_rhs(const DevNet& net, int ncell, const double* cellpar, const double* y, const double* rates,
@@ -40,6 +42,9 @@ struct racg_handle {
   int* d_queue = nullptr;
   unsigned long long* d_phase = nullptr;
   long launches = 0;
+  // warm scheduling: per-cell cost of the previous batch and the queue order derived from it
+  float* d_cost = nullptr; int* d_order = nullptr; int cost_cap = 0, cost_n = 0;
+  std::vector<float> h_cost; std::vector<int> h_order;
   double* dbg_J = nullptr;   // set only inside racg_debug_fjac
   double dbg_con = 0.0;
 };
@@ -267,6 +272,7 @@ int racg_destroy(racg_handle* h) {
   if (h->device >= 0) {
     for (void* p : h->allocs) cudaFree(p);
     cudaFree(h->d_ws); cudaFree(h->d_queue); cudaFree(h->d_phase);
+    if (h->d_cost) { cudaFree(h->d_cost); cudaFree(h->d_order); }
   }
   delete h;
   return 0;
@@ -366,11 +372,34 @@ int racg_solve_batch_dev(racg_handle* h, int ncell, const double* cellpar, const
   a.nrec_real = nrec_real; a.istate = istate; a.quality = quality; a.stats = stats;
   a.queue = h->d_queue; a.ws = h->d_ws; a.ws_stride = h->ws_stride; a.phase = h->d_phase;
   a.dbg_J = h->dbg_J; a.dbg_con = h->dbg_con;
+  if (h->cost_cap < ncell) {
+    if (h->d_cost) { cudaFree(h->d_cost); cudaFree(h->d_order); }
+    CK(cudaMalloc(&h->d_cost, sizeof(float) * ncell)); CK(cudaMalloc(&h->d_order, sizeof(int) * ncell));
+    h->cost_cap = ncell; h->cost_n = 0;
+  }
+  if (h->cost_n == ncell && !h->dbg_J && !getenv("RACG_NO_WARM_ORDER")) {
+    // same batch size as the previous call: serve the queue heaviest first (order only, results
+    // do not depend on it)
+    h->h_cost.resize(ncell); h->h_order.resize(ncell);
+    CK(cudaMemcpyAsync(h->h_cost.data(), h->d_cost, sizeof(float) * ncell, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < ncell; ++i) h->h_order[i] = i;
+    const float* cst = h->h_cost.data();
+    std::stable_sort(h->h_order.begin(), h->h_order.end(), [cst](int x, int y) { return cst[x] > cst[y]; });
+    CK(cudaMemcpyAsync(h->d_order, h->h_order.data(), sizeof(int) * ncell, cudaMemcpyHostToDevice, st));
+    a.order = h->d_order;
+  }
   CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), st));
   CK(cudaMemsetAsync(h->d_phase, 0, RACG_NPHASE * sizeof(unsigned long long), st));
   int nblocks = ncell < h->nblocks ? ncell : h->nblocks;
   CK(launch_integrate(h->dn, a, nblocks, h->smem_int, st));
   h->launches += 1;
+  if (!h->dbg_J) {
+    launch_cost(ncell, stats, h->d_cost, st);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    h->cost_n = ncell;
+  }
   return 0;
 }
 

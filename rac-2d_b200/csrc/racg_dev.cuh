@@ -107,6 +107,7 @@ struct BatchArgs {
   double* stats;             // [NSTAT][ncell]
   // scheduler + workspace
   int* queue;                // work-queue counter
+  const int* order;          // optional: queue position -> cell (heaviest first), else identity
   double* ws;                // per-CTA workspace
   size_t ws_stride;          // doubles per CTA
   unsigned long long* phase; // [RACG_NPHASE] cycle counters

@@ -1371,8 +1371,8 @@ integrate_kernel(const BatchArgs args) {
     __syncthreads();
     if (tid == 0) s_cell = atomicAdd(args.queue, 1);
     __syncthreads();
-    const int cell = s_cell;
-    if (cell >= ncell) break;
+    if (s_cell >= ncell) break;
+    const int cell = args.order ? args.order[s_cell] : s_cell;
     long long tc = clock64();
     // ---- load the cell
     if (tid < RACG_NPAR) sm.par[tid] = args.cellpar[(size_t)tid * ncell + cell];
@@ -1997,6 +1997,18 @@ integrate_kernel(const BatchArgs args) {
 //   [0, xlow)            scratch of f / Jacobian / SpMV partials / tail_lu buffers / inverse scratch
 //   [sinv, +nblkS*33*32) inverses of the S diagonal blocks (column-major, ld 33)
 //   [tab, +blob)         tables of the staged head solves
+// cost of every cell of the batch just integrated (in units of one triangular solve), kept by
+// the handle: when the next batch has the same number of cells -- the disk code re-integrates
+// the same grid every structure iteration -- its work queue is served heaviest first
+__global__ void cost_kernel(int ncell, const double* __restrict__ stats, float* __restrict__ cost) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncell) cost[c] = (float)(10.0 * stats[(size_t)3 * ncell + c] + stats[(size_t)5 * ncell + c] +
+                                   0.5 * stats[(size_t)1 * ncell + c]);
+}
+void launch_cost(int ncell, const double* stats, float* cost, cudaStream_t st) {
+  cost_kernel<<<(ncell + 255) / 256, 256, 0, st>>>(ncell, stats, cost);
+}
+
 size_t integrate_smem_bytes(DevNet& net) {
   if (net.glu.on) {
     const size_t n = net.n, R = net.R;
