@@ -36,7 +36,7 @@ struct EllDev {
 // constant-cache miss.
 struct GluDev {
   int on, nlev, zpos, voff;
-  int subst;                  // 1: triangular substitution inside the diagonal blocks instead of explicit inverses
+  int subst;                  // bits: 1 L blocks, 2 U blocks of the tail, 8 U blocks of the S rows by substitution
   int ngrp, ndesc, doff;      // descriptor block: [lvl (nlev+1) | grp (ngrp) | stages (nst) | rank-1 pairs]; doff = offset in smem (doubles)
   const uint32_t* piv; const uint32_t* mul; const uint32_t* ent; const uint16_t* tgt;
   const uint16_t* r1tgt;      // rank-1 levels: 4 target positions per (row chunk, column chunk, lane)

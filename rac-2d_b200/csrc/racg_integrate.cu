@@ -501,7 +501,7 @@ __device__ __forceinline__ void tri_inv_upper(const double* src, int ld, int bs,
 // head (dense copies at X + sinv, ld 33) and the blocks of the dense tail (ld ldt).  After the
 // call the strictly-lower part of a block holds L^-1 (unit diagonal implicit) and the upper
 // part U^-1.  One warp per job, two jobs (L, U) per block, scratch = NW/2 tiles at X.
-__device__ __noinline__ void block_inverses() {
+__device__ __noinline__ void block_inverses(int subst) {
   const DevNet& net = c_net;
   const GSm sm = glu_smem();
   const int nt = net.nt, ldt = net.ldt, nbT = (nt + 31) >> 5, nbS = net.ss.nblkS;
@@ -509,7 +509,8 @@ __device__ __noinline__ void block_inverses() {
   double* zs = sm.X + (w >> 1) * (33 * 32);
   for (int job0 = 0; job0 < 2 * (nbS + nbT); job0 += NW) {
     const int job = job0 + w, blk = job >> 1, upper = job & 1;
-    const bool act = job < 2 * (nbS + nbT);
+    const int sbit = upper ? ((job >> 1) < nbS ? 8 : 2) : 1;
+    const bool act = job < 2 * (nbS + nbT) && !(subst & sbit);   // triangles solved by substitution stay as they are
     double* D = sm.X; int ld = 33, bs = 32;
     if (act) {
       if (blk < nbS) D = sm.X + net.ss.sinv + blk * (33 * 32);
@@ -773,7 +774,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
     case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
   }
   const long long t2b = clock64();
-  if (!subst) block_inverses();
+  if ((subst & 11) != 11) block_inverses(subst);
   const int res = *flag;
   __syncthreads();
   if (tid == 0) {
@@ -972,19 +973,34 @@ __device__ __forceinline__ double block_apply(const double* T, int ld, int bs, b
   return upper ? mv : mv + tmp[r < 32 ? r : 0];
 }
 
-// in-block triangular substitution by one warp (lane r owns row r); T column-major, ld
+// in-block triangular substitution by one warp (lane r owns row r); T column-major, ld.
+// The lane's row of the triangle is fetched into registers first, so that the 32 dependent
+// steps are one shuffle and one FMA each.  Used for the U blocks: their explicit inverses
+// mix pivots of very different size and cost the hottest cells (T > 1700 K) their
+// convergence (78 k instead of 1.8 k steps were measured); L blocks keep the inverses.
 __device__ __forceinline__ double block_subst(const double* T, int ld, int bs, bool upper, double v, int r) {
   if (!upper) {
-    for (int c = 0; c < bs; ++c) {
-      const double xc = __shfl_sync(0xffffffffu, v, c);
-      if (r > c && r < bs) v -= T[c * ld + r] * xc;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double row[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const int c = 16 * h + q; row[q] = (c < r && r < bs) ? T[c * ld + r] : 0.0; }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const double xc = __shfl_sync(0xffffffffu, v, 16 * h + q); v -= row[q] * xc; }
     }
   } else {
     const double rd = (r < bs) ? 1.0 / T[r * ld + r] : 1.0;
-    for (int c = bs - 1; c >= 0; --c) {
-      if (r == c) v = v * rd;
-      const double xc = __shfl_sync(0xffffffffu, v, c);
-      if (r < c) v -= T[c * ld + r] * xc;
+#pragma unroll
+    for (int h = 1; h >= 0; --h) {
+      double row[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const int c = 16 * h + q; row[q] = (c > r && c < bs) ? T[c * ld + r] : 0.0; }
+#pragma unroll
+      for (int q = 15; q >= 0; --q) {
+        if (r == 16 * h + q) v = v * rd;
+        const double xc = __shfl_sync(0xffffffffu, v, 16 * h + q);
+        v -= row[q] * xc;
+      }
     }
   }
   return v;
@@ -1020,7 +1036,7 @@ __device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const ui
   }
   if (sub == 0) tmp[r] = (r < nrows) ? sm.xb[row] - acc : 0.0;
   __syncthreads();
-  if (subst) {
+  if (subst & (upper ? 8 : 1)) {
     if (tid < 32) {
       const double xv = block_subst(sm.X + net.ss.sinv + blk * (33 * 32), 33, 32, upper, tmp[tid], tid);
       if (tid < nrows) sm.xb[rows[S.z + tid]] = xv;
@@ -1117,7 +1133,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst)
       const double acc = group_sum(a0 + a1, 8);
       if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
       __syncthreads();
-      if (subst) {
+      if (subst & 1) {
         if (tid < 32) { const double xv = block_subst(sm.Dt + (o * ldt + o), ldt, bs, false, tmp[tid], tid); if (tid < bs) xt[o + tid] = xv; }
       } else {
         const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, false, tmp, r, sg);
@@ -1137,7 +1153,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst)
       const double acc = group_sum(a0 + a1, 8);
       if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
       __syncthreads();
-      if (subst) {
+      if (subst & 2) {
         if (tid < 32) { const double xv = block_subst(sm.Dt + (o * ldt + o), ldt, bs, true, tmp[tid], tid); if (tid < bs) xt[o + tid] = xv; }
       } else {
         const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, true, tmp, r, sg);
@@ -1448,7 +1464,7 @@ integrate_kernel(const BatchArgs args) {
     double t = t_start, t_step = args.dt_first[cell], tout = t + t_step;
     int NERR = 0, nerr_c = 0, quality = 0, ISTATE = 1, n_record_real = 1;
     long long aNST = 0, aNFE = 0, aNJE = 0, aNLU = 0, nrestart = 0;
-    const int subst = net.glu.subst;   // diagnostics: substitution instead of inverse blocks (RACG_SUBST=1)
+    const int subst = net.glu.subst;   // RACG_SUBST bits: 1 = L blocks, 2 = U blocks of the tail, 8 = U blocks of the S rows by substitution
     Lsodes s;
     s.NST = s.NFE = s.NJE = s.NLU = s.NQU = 0; s.HU = 0.0; s.INIT = 0; s.IMXER = 0;
     s.n_solve = s.n_cfail = s.n_efail = 0; s.wiped = 0; s.pw = 0.0;
