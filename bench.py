@@ -144,7 +144,8 @@ def main():
     ap.add_argument("--cpu-jac-mode", type=int, default=1,
                     help="1 = reference-faithful O(NEQ*R) Jacobian (default), 0 = O(R) Jacobian")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel-ncell", type=int, default=65536, help="cells for the K2/K3 roofline kernels")
+    ap.add_argument("--kernel-ncell", type=int, default=75776,
+                    help="cells for the K1-K3 roofline kernels (148 SMs x 128-cell tiles x 4 waves)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -30,7 +30,7 @@ rates_kernel(const DevNet net, int ncell, const double* __restrict__ cellpar, do
 //            (rates streamed once from HBM, 8*TC contiguous bytes per reaction)
 //   phase 2: segmented-ELL gather over species (net stoichiometry), writes ydot
 template <int TC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 rhs_kernel(const DevNet net, int ncell, const double* __restrict__ cellpar,
            const double* __restrict__ y, const double* __restrict__ rates, double* __restrict__ ydot) {
   extern __shared__ __align__(16) double sm[];
@@ -45,29 +45,42 @@ rhs_kernel(const DevNet net, int ncell, const double* __restrict__ cellpar,
     const int cell = tile * TC + c;
     const bool ok = cell < ncell;
     __syncthreads();
-    for (int i = q; i < n; i += NQ) ys[(size_t)i * TC + c] = ok ? y[(size_t)i * ncell + cell] : 0.0;
+#pragma unroll 8
+    for (int i = q; i < n; i += NQ) ys[(size_t)i * TC + c] = ok ? __ldcs(y + (size_t)i * ncell + cell) : 0.0;
     if (q == 0) ds[c] = ok ? cellpar[(size_t)RACG_P_ratioDust2HnucNum * ncell + cell] *
                               cellpar[(size_t)RACG_P_SitesPerGrain * ncell + cell] : 1.0;
     __syncthreads();
     const double DS = ds[c];
-    for (int r = q; r < R; r += NQ) {
-      const uint32_t w = __ldg(net.fw + r);
-      const double k = ok ? __ldcs(rates + (size_t)r * ncell + cell) : 0.0;
-      // flux_of with the tile-strided y
-      const int kind = (w >> 20) & 3;
-      const double y1 = ys[(size_t)(w & 1023) * TC + c];
-      double f;
-      if (kind == FK_ONE) f = k * y1;
-      else if (kind == FK_TWO) {
-        const double y2 = ys[(size_t)((w >> 10) & 1023) * TC + c];
-        f = k * y1 * y2;
-        if (y1 < 0.0 && y2 < 0.0) f = -f;
-      } else if (kind == FK_SAT) {
-        const double tmp1 = DS * net.sat_c[w >> 22];
-        if (tmp1 <= 0.0) f = k;
-        else { const double tmp = y1 / tmp1; f = (tmp <= 1e-4) ? k * tmp : k * (1.0 - exp(-tmp)); }
-      } else f = 0.0;
-      fx[(size_t)r * TC + c] = f;
+    for (int r0 = q; r0 < R; r0 += 8 * NQ) {
+      uint32_t wv[8]; double kv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u * NQ;
+        wv[u] = (r < R) ? __ldg(net.fw + r) : (3u << 20);
+        kv[u] = (r < R && ok) ? __ldcs(rates + (size_t)r * ncell + cell) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u * NQ;
+        if (r >= R) continue;
+        const uint32_t w = wv[u];
+        const double k = kv[u];
+        // flux_of with the tile-strided y
+        const int kind = (w >> 20) & 3;
+        const double y1 = ys[(size_t)(w & 1023) * TC + c];
+        double f;
+        if (kind == FK_ONE) f = k * y1;
+        else if (kind == FK_TWO) {
+          const double y2 = ys[(size_t)((w >> 10) & 1023) * TC + c];
+          f = k * y1 * y2;
+          if (y1 < 0.0 && y2 < 0.0) f = -f;
+        } else if (kind == FK_SAT) {
+          const double tmp1 = DS * net.sat_c[w >> 22];
+          if (tmp1 <= 0.0) f = k;
+          else { const double tmp = y1 / tmp1; f = (tmp <= 1e-4) ? k * tmp : k * (1.0 - exp(-tmp)); }
+        } else f = 0.0;
+        fx[(size_t)r * TC + c] = f;
+      }
     }
     __syncthreads();
     // gather: work item = (sub-row, cell)
@@ -81,10 +94,15 @@ rhs_kernel(const DevNet net, int ncell, const double* __restrict__ cellpar,
       // true length of this sub-row is unknown here; padded entries carry coef 0
       const int width = g.blk_width[b];
       double acc = 0.0;
-      for (int j = 0; j < width; ++j) {
-        const uint32_t v = __ldg(e + j * 32);
-        const int cf = (int)(v >> 24) - 4;
-        if (cf != 0) acc += (double)cf * fx[(size_t)(v & 0xffffffu) * TC + c];
+      for (int j0 = 0; j0 < width; j0 += 8) {
+        uint32_t ev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[j] = (j0 + j < width) ? __ldg(e + (j0 + j) * 32) : (4u << 24);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int cf = (int)(ev[j] >> 24) - 4;
+          if (cf != 0) acc += (double)cf * fx[(size_t)(ev[j] & 0xffffffu) * TC + c];
+        }
       }
       if (t >= 0) { if (ok) __stcs(ydot + (size_t)t * ncell + cell, acc); }
       else px[(size_t)(-2 - t) * TC + c] = acc;
@@ -124,31 +142,47 @@ jac_kernel(const DevNet net, const JacColTables jc, int ncell, const double* __r
     for (int g = 0; g < jc.ngroups; ++g) {
       __syncthreads();
       const int pb = jc.grp_pair_ptr[g], pe = jc.grp_pair_ptr[g + 1];
-      for (int p = pb + w; p < pe; p += NWARP) {
-        const uint32_t pr = __ldg(jc.pair + p);
-        const int r = pr & 0xffff, which = pr >> 16;
-        const uint32_t fwv = __ldg(net.fw + r);
-        const int kind = (fwv >> 20) & 3;
-        const int r1 = fwv & 1023, r2 = (fwv >> 10) & 1023;
-        const double k = ok ? __ldg(rates + (size_t)r * ncell + cell) : 0.0;
-        double d = 0.0;
-        if (kind == FK_ONE) d = k;
-        else if (kind == FK_TWO) {
-          const double y1 = ok ? __ldg(y + (size_t)r1 * ncell + cell) : 0.0;
-          const double y2 = (r2 == r1) ? y1 : (ok ? __ldg(y + (size_t)r2 * ncell + cell) : 0.0);
-          if (r1 != r2) d = (which == 0) ? k * y2 : k * y1;
-          else d = 2.0 * k * y2;
-          if (y1 < 0.0 && y2 < 0.0) d = -d;
-        } else if (kind == FK_SAT) {
-          const double tmp2 = DS * net.sat_c[fwv >> 22];
-          if (tmp2 > 0.0) {
-            const double tmp1 = 1.0 / tmp2;
-            const double y1 = ok ? __ldg(y + (size_t)r1 * ncell + cell) : 0.0;
-            const double tmp = y1 * tmp1;
-            d = (tmp <= 1e-4) ? k * tmp1 : k * tmp1 * exp(-tmp);
-          }
+      for (int p0 = pb + w; p0 < pe; p0 += 4 * NWARP) {
+        uint32_t fwv4[4]; int which4[4]; double k4[4], ya4[4], yb4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + u * NWARP;
+          const bool on = p < pe;
+          const uint32_t pr = on ? __ldg(jc.pair + p) : 0u;
+          const int r = pr & 0xffff;
+          which4[u] = pr >> 16;
+          fwv4[u] = on ? __ldg(net.fw + r) : (3u << 20);
+          k4[u] = (on && ok) ? __ldg(rates + (size_t)r * ncell + cell) : 0.0;
+          const int kind = (fwv4[u] >> 20) & 3;
+          const int r1 = fwv4[u] & 1023, r2 = (fwv4[u] >> 10) & 1023;
+          ya4[u] = (on && ok && kind != FK_ONE) ? __ldg(y + (size_t)r1 * ncell + cell) : 0.0;
+          yb4[u] = (on && ok && kind == FK_TWO && r2 != r1) ? __ldg(y + (size_t)r2 * ncell + cell) : ya4[u];
         }
-        dbuf[(size_t)(p - pb) * 32 + l] = d;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + u * NWARP;
+          if (p >= pe) continue;
+          const uint32_t fwv = fwv4[u];
+          const int kind = (fwv >> 20) & 3, which = which4[u];
+          const int r1 = fwv & 1023, r2 = (fwv >> 10) & 1023;
+          const double k = k4[u];
+          double d = 0.0;
+          if (kind == FK_ONE) d = k;
+          else if (kind == FK_TWO) {
+            const double y1 = ya4[u], y2 = yb4[u];
+            if (r1 != r2) d = (which == 0) ? k * y2 : k * y1;
+            else d = 2.0 * k * y2;
+            if (y1 < 0.0 && y2 < 0.0) d = -d;
+          } else if (kind == FK_SAT) {
+            const double tmp2 = DS * net.sat_c[fwv >> 22];
+            if (tmp2 > 0.0) {
+              const double tmp1 = 1.0 / tmp2;
+              const double tmp = ya4[u] * tmp1;
+              d = (tmp <= 1e-4) ? k * tmp1 : k * tmp1 * exp(-tmp);
+            }
+          }
+          dbuf[(size_t)(p - pb) * 32 + l] = d;
+        }
       }
       __syncthreads();
       const int sb = jc.grp_slot_ptr[g], se = jc.grp_slot_ptr[g + 1];
@@ -160,6 +194,109 @@ jac_kernel(const DevNet net, const JacColTables jc, int ncell, const double* __r
           acc += (double)((int)(v >> 24) - 4) * dbuf[(size_t)(v & 0xffffffu) * 32 + l];
         }
         if (ok) __stcs(pd + (size_t)jc.slot_id[s] * ncell + cell, acc);
+      }
+    }
+  }
+}
+
+// K3, wide variant (ncell % 4 == 0): a lane owns 4 consecutive cells (32-byte vector loads and
+// stores, 1 KB contiguous per warp access), a CTA of 32 warps a tile of 128 cells, so that every
+// Jacobian slot row is written in 1 KB pieces and each instruction moves 4x the bytes.
+struct D4 { double v[4]; };
+__device__ __forceinline__ D4 ld4(const double* p, bool ok) {
+  D4 r;
+  if (ok) { const double2 a = __ldg((const double2*)p), b = __ldg((const double2*)p + 1); r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; }
+  else { r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0; }
+  return r;
+}
+__global__ void __launch_bounds__(1024)
+jac_kernel4(const DevNet net, const JacColTables jc, int ncell, const double* __restrict__ cellpar,
+            const double* __restrict__ y, const double* __restrict__ rates, double* __restrict__ pd) {
+  extern __shared__ __align__(16) double sm[];
+  const int NWARP = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double* dbuf = sm;   // [max_pairs][128]
+  for (int tile = blockIdx.x; tile * 128 < ncell; tile += gridDim.x) {
+    const int cell = tile * 128 + 4 * l;
+    const bool ok = cell < ncell;          // ncell % 4 == 0: all four cells or none
+    const D4 a1 = ld4(cellpar + (size_t)RACG_P_ratioDust2HnucNum * ncell + cell, ok);
+    const D4 a2 = ld4(cellpar + (size_t)RACG_P_SitesPerGrain * ncell + cell, ok);
+    double DS[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) DS[q] = ok ? a1.v[q] * a2.v[q] : 1.0;
+    if (ok) {
+      const double2 z2 = make_double2(0.0, 0.0);
+      for (int z = w; z < jc.nzero; z += NWARP) {
+        double2* o = (double2*)(pd + (size_t)jc.zero_slots[z] * ncell + cell);
+        __stcs(o, z2); __stcs(o + 1, z2);
+      }
+    }
+    for (int g = 0; g < jc.ngroups; ++g) {
+      __syncthreads();
+      const int pb = jc.grp_pair_ptr[g], pe = jc.grp_pair_ptr[g + 1];
+      for (int p0 = pb + w; p0 < pe; p0 += 2 * NWARP) {
+        uint32_t fwv2[2]; int which2[2]; D4 k2[2], ya2[2], yb2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int p = p0 + u * NWARP;
+          const bool on = p < pe;
+          const uint32_t pr = on ? __ldg(jc.pair + p) : 0u;
+          const int r = pr & 0xffff;
+          which2[u] = pr >> 16;
+          fwv2[u] = on ? __ldg(net.fw + r) : (3u << 20);
+          const int kind = (fwv2[u] >> 20) & 3;
+          const int r1 = fwv2[u] & 1023, r2 = (fwv2[u] >> 10) & 1023;
+          k2[u] = ld4(rates + (size_t)r * ncell + cell, on && ok);
+          ya2[u] = ld4(y + (size_t)r1 * ncell + cell, on && ok && kind != FK_ONE);
+          yb2[u] = (kind == FK_TWO && r2 != r1) ? ld4(y + (size_t)r2 * ncell + cell, on && ok) : ya2[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int p = p0 + u * NWARP;
+          if (p >= pe) continue;
+          const uint32_t fwv = fwv2[u];
+          const int kind = (fwv >> 20) & 3, which = which2[u];
+          const int r1 = fwv & 1023, r2 = (fwv >> 10) & 1023;
+          double d[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double k = k2[u].v[q];
+            double dd = 0.0;
+            if (kind == FK_ONE) dd = k;
+            else if (kind == FK_TWO) {
+              const double y1 = ya2[u].v[q], y2 = yb2[u].v[q];
+              if (r1 != r2) dd = (which == 0) ? k * y2 : k * y1;
+              else dd = 2.0 * k * y2;
+              if (y1 < 0.0 && y2 < 0.0) dd = -dd;
+            } else if (kind == FK_SAT) {
+              const double tmp2 = DS[q] * net.sat_c[fwv >> 22];
+              if (tmp2 > 0.0) {
+                const double tmp1 = 1.0 / tmp2;
+                const double tmp = ya2[u].v[q] * tmp1;
+                dd = (tmp <= 1e-4) ? k * tmp1 : k * tmp1 * exp(-tmp);
+              }
+            }
+            d[q] = dd;
+          }
+          double2* o = (double2*)(dbuf + (size_t)(p - pb) * 128 + 4 * l);
+          o[0] = make_double2(d[0], d[1]); o[1] = make_double2(d[2], d[3]);
+        }
+      }
+      __syncthreads();
+      const int sb = jc.grp_slot_ptr[g], se = jc.grp_slot_ptr[g + 1];
+      const bool accum = jc.grp_accum[g] != 0;
+      for (int s = sb + w; s < se; s += NWARP) {
+        const int slot = __ldg(jc.slot_id + s), e0 = __ldg(jc.slot_ent_ptr + s), e1 = __ldg(jc.slot_ent_ptr + s + 1);
+        double* op = pd + (size_t)slot * ncell + cell;
+        D4 acc = ld4(op, accum && ok);
+        for (int e = e0; e < e1; ++e) {
+          const uint32_t v = __ldg(jc.ent + e);
+          const double cf = (double)((int)(v >> 24) - 4);
+          const double2* dp = (const double2*)(dbuf + (size_t)(v & 0xffffffu) * 128 + 4 * l);
+          const double2 da = dp[0], db = dp[1];
+          acc.v[0] += cf * da.x; acc.v[1] += cf * da.y; acc.v[2] += cf * db.x; acc.v[3] += cf * db.y;
+        }
+        if (ok) { __stcs((double2*)op, make_double2(acc.v[0], acc.v[1])); __stcs((double2*)op + 1, make_double2(acc.v[2], acc.v[3])); }
       }
     }
   }
@@ -181,12 +318,22 @@ cudaError_t launch_rhs(const DevNet& net, int ncell, const double* cellpar, cons
   if (e != cudaSuccess) return e;
   int ntiles = (ncell + RHS_TC - 1) / RHS_TC;
   int grid = ntiles < nsm ? ntiles : nsm;
-  rhs_kernel<RHS_TC><<<grid, 256, smem, st>>>(net, ncell, cellpar, y, rates, ydot);
+  rhs_kernel<RHS_TC><<<grid, 1024, smem, st>>>(net, ncell, cellpar, y, rates, ydot);
   return cudaGetLastError();
 }
 
 cudaError_t launch_jac(const DevNet& net, const JacColTables& jc, int ncell, const double* cellpar, const double* y,
                        const double* rates, double* pd, int nsm, cudaStream_t st) {
+  const size_t smem4 = (size_t)jc.max_pairs * 128 * sizeof(double);
+  if (ncell % 4 == 0 && smem4 <= 226 * 1024 && ((size_t)pd % 32) == 0 && ((size_t)y % 32) == 0 &&
+      ((size_t)rates % 32) == 0 && ((size_t)cellpar % 32) == 0) {
+    cudaError_t e4 = cudaFuncSetAttribute(jac_kernel4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+    if (e4 != cudaSuccess) return e4;
+    const int ntiles4 = (ncell + 127) / 128;
+    const int per_sm4 = (smem4 + 1024) * 2 <= 227 * 1024 ? 2 : 1;
+    jac_kernel4<<<ntiles4 < nsm * per_sm4 ? ntiles4 : nsm * per_sm4, 1024, smem4, st>>>(net, jc, ncell, cellpar, y, rates, pd);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)jc.max_pairs * 32 * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

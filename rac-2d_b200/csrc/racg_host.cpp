@@ -715,7 +715,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   // derivatives fit the shared-memory buffer; hub columns are cut into chunks that
   // accumulate into pd.
   {
-    const int CAP = 192;
+    const int CAP = getenv("RACG_JAC_CAP") ? atoi(getenv("RACG_JAC_CAP")) : 192;
     HostNet::JacCols& jc = hn.jc;
     std::vector<std::vector<uint32_t>> col_pairs(NEQ);
     for (int i = 0; i < R; ++i) {
