@@ -1383,9 +1383,10 @@ integrate_kernel(const BatchArgs args) {
   // element e of this thread is species i = tid + e*NT
   double yh[EPT][6], acor[EPT], ewt[EPT], rt[EPT], at[EPT];
 #define FORE _Pragma("unroll") for (int e = 0, i = tid; e < EPT; ++e, i += NT) if (i < n)
+  int redo_mask = -1;   // >= 0: integrate the same cell again with this block-solve mode
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_cell = atomicAdd(args.queue, 1);
+    if (tid == 0 && redo_mask < 0) s_cell = atomicAdd(args.queue, 1);
     __syncthreads();
     if (s_cell >= ncell) break;
     const int cell = args.order ? args.order[s_cell] : s_cell;
@@ -1464,7 +1465,14 @@ integrate_kernel(const BatchArgs args) {
     double t = t_start, t_step = args.dt_first[cell], tout = t + t_step;
     int NERR = 0, nerr_c = 0, quality = 0, ISTATE = 1, n_record_real = 1;
     long long aNST = 0, aNFE = 0, aNJE = 0, aNLU = 0, nrestart = 0;
-    const int subst = net.glu.subst;   // RACG_SUBST bits: 1 = L blocks, 2 = U blocks of the tail, 8 = U blocks of the S rows by substitution
+    // block-solve mode (RACG_SUBST bits: 1 = L blocks, 2 = U blocks of the tail, 8 = U blocks of the
+    // S rows by substitution instead of explicit inverses).  On a few very stiff, hot cells one
+    // mode or the other lets round-off in the linear solves defeat the corrector (thousands of
+    // convergence failures where the reference algorithm has none): such a cell is integrated
+    // again from its initial state with the tail's U blocks treated the other way.
+    const bool second_try = redo_mask >= 0;
+    const int subst = second_try ? redo_mask : net.glu.subst;
+    redo_mask = -1;
     Lsodes s;
     s.NST = s.NFE = s.NJE = s.NLU = s.NQU = 0; s.HU = 0.0; s.INIT = 0; s.IMXER = 0;
     s.n_solve = s.n_cfail = s.n_efail = 0; s.wiped = 0; s.pw = 0.0;
@@ -1957,6 +1965,8 @@ integrate_kernel(const BatchArgs args) {
       __syncthreads();
       record_out(irec);
       n_record_real = irec;
+      if (GLU && !second_try && s.n_cfail > 6000) { redo_mask = subst ^ 2; break; }
+      if (aNST + s.NST > 500000) break;   // runaway guard: 5x the heaviest cell that completes normally
       if (t >= t_max) break;
       if (ISTATE < 0) {
         NERR += 1; nerr_c += 1;
@@ -1981,6 +1991,7 @@ integrate_kernel(const BatchArgs args) {
       t_step = t_step * ratio;
       tout = t + t_step;
     }
+    if (redo_mask >= 0) continue;
     aNST += s.NST; aNFE += s.NFE; aNJE += s.NJE; aNLU += s.NLU;
     // records after an early exit are filled with the last state (src/chemistry.f90:570-575)
     for (int r2 = n_record_real + 1; r2 <= args.sp.nrec_max; ++r2) record_out(r2);
