@@ -1384,6 +1384,7 @@ integrate_kernel(const BatchArgs args) {
   double yh[EPT][6], acor[EPT], ewt[EPT], rt[EPT], at[EPT];
 #define FORE _Pragma("unroll") for (int e = 0, i = tid; e < EPT; ++e, i += NT) if (i < n)
   int redo_mask = -1;   // >= 0: integrate the same cell again with this block-solve mode
+  long long cNST = 0, cNFE = 0, cNJE = 0, cNLU = 0, cSOL = 0, cCF = 0, cEF = 0;   // work of the abandoned attempt
   for (;;) {
     __syncthreads();
     if (tid == 0 && redo_mask < 0) s_cell = atomicAdd(args.queue, 1);
@@ -1991,8 +1992,15 @@ integrate_kernel(const BatchArgs args) {
       t_step = t_step * ratio;
       tout = t + t_step;
     }
-    if (redo_mask >= 0) continue;
-    aNST += s.NST; aNFE += s.NFE; aNJE += s.NJE; aNLU += s.NLU;
+    if (redo_mask >= 0) {
+      cNST = aNST + s.NST; cNFE = aNFE + s.NFE; cNJE = aNJE + s.NJE; cNLU = aNLU + s.NLU;
+      cSOL = s.n_solve; cCF = s.n_cfail; cEF = s.n_efail;
+      continue;
+    }
+    // the counters report all the work done for the cell, an abandoned first attempt included
+    aNST += s.NST + cNST; aNFE += s.NFE + cNFE; aNJE += s.NJE + cNJE; aNLU += s.NLU + cNLU;
+    s.n_solve += (int)cSOL; s.n_cfail += (int)cCF; s.n_efail += (int)cEF;
+    cNST = cNFE = cNJE = cNLU = cSOL = cCF = cEF = 0;
     // records after an early exit are filled with the last state (src/chemistry.f90:570-575)
     for (int r2 = n_record_real + 1; r2 <= args.sp.nrec_max; ++r2) record_out(r2);
     if (NERR > (int)(0.1f * (float)n_record_formula)) quality += 1;
