@@ -89,6 +89,12 @@ def algorithmic_bytes(stats, R, NEQ, NNZ, nnz_lu):
     return nfe * b_k2 + nje * b_k3 + nlu * b_k4 + nsolve * b_k5 + nst * b_step
 
 
+def workload_text(ncell, network, R, NEQ, NNZ):
+    return (f"configs[1]: {ncell} synthetic cells per GPU, {network} (R={R}, NEQ={NEQ}, NNZ={NNZ}), "
+            f"Garrod08 waterice IC, t=1e-8..1e6 yr, RTOL 1e-4 ATOL 1e-30 (policy j=1), mxstep 6000, "
+            f"reset every 50 outputs, evolT=F")
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the reference algorithm on the host cores (the Fortran
     `rac` cannot be built: no Fortran compiler in the image).  Rank 0 only."""
@@ -119,8 +125,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"configs[1]: 1e4 synthetic cells, {args.network}, 1e-8..1e6 yr, RTOL 1e-4 ATOL 1e-30",
-                   "cells_per_step": nsample},
+        "config": {"workload": workload_text(args.ncell, args.network, onet.R, onet.NEQ, onet.NNZ),
+                   "cells_per_gpu": args.ncell, "seed": synth.SEED,
+                   "cells_per_step": nsample,
+                   "note": "each step integrates a bounded sample (the first cells_per_step cells) of the workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"first {nsample} cells of the same synthetic stream per step, "
                                    f"oracle C++ port of chem_evol_solve+DLSODES, jac_mode={args.cpu_jac_mode} "
@@ -322,9 +330,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {ncell} synthetic cells per GPU, {args.network} "
-                                   f"(R={R}, NEQ={NEQ}, NNZ={sol.NNZ}), Garrod08 waterice IC, t=1e-8..1e6 yr, "
-                                   f"RTOL 1e-4 ATOL 1e-30 (policy j=1), mxstep 6000, reset every 50 outputs, evolT=F",
+            "config": {"workload": workload_text(ncell, args.network, R, NEQ, sol.NNZ),
                        "cells_per_gpu": ncell, "seed": rb.synth.SEED,
                        "sharding": "first n_gpus*cells_per_gpu cells of the stream, dealt round-robin to the ranks",
                        "scheduling": "work queue served heaviest-first from the previous step's per-cell cost",

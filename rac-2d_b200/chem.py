@@ -299,7 +299,7 @@ class ChemSolver:
     def phase_cycles(self):
         out = np.zeros(32)
         _check(lib().racg_phase_cycles(self.h, _p(out)))
-        names = ["rates", "f", "jac", "fact_head", "fact_schur", "fact_tail", "solve", "vec", "io",
+        names = ["rates", "f", "jac", "fact_head", "fact_schur", "fact_tail", "solve", "vec", "glu_loop",
                  "total", "ncell", "pbuild", "tail_inv", "solve_fwd", "solve_tail", "solve_bwd",
                  "f_flux", "f_gather", "glu_pivmul", "glu_flat", "glu_narrow", "glu_wide", "solve_spmv", "glu_copy"]
         return {n: out[i] for i, n in enumerate(names)}

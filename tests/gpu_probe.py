@@ -23,13 +23,13 @@ for rep in range(2):
 print("mean NST %.0f NFE %.0f NJE %.0f NLU %.0f nsolve %.0f ; max NST %.0f" % (st[:,0].mean(), st[:,1].mean(), st[:,2].mean(), st[:,3].mean(), st[:,5].mean(), st[:,0].max()))
 ph = sol.phase_cycles()
 tot = ph["total"]
-print("phase share of CTA cycles:", {k: round(v / tot, 4) for k, v in ph.items() if k in ("rates","f","jac","fact_head","fact_schur","fact_tail","solve","vec","io")})
+print("phase share of CTA cycles:", {k: round(v / tot, 4) for k, v in ph.items() if k in ("rates","f","jac","fact_head","fact_schur","fact_tail","solve","vec","glu_loop")})
 print("cycles per cell (sum over CTAs / ncell): %.3e" % (tot / max(ph["ncell"], 1)))
 nlu, nsolve, nfe, nje, nst = st[:,3].sum(), st[:,5].sum(), st[:,1].sum(), st[:,2].sum(), st[:,0].sum()
 print("pbuild/LU %.0f tail_inv/LU %.0f ; solve fwd %.0f tail %.0f bwd %.0f" % (ph["pbuild"]/nlu, ph["tail_inv"]/nlu, ph["solve_fwd"]/nsolve, ph["solve_tail"]/nsolve, ph["solve_bwd"]/nsolve))
 print("per LU: glu_pivmul %.0f flat %.0f narrow %.0f wide %.0f copy %.0f | per solve: spmv %.0f | per f: flux %.0f gather %.0f" % (
     ph["glu_pivmul"]/nlu, ph["glu_flat"]/nlu, ph["glu_narrow"]/nlu, ph["glu_wide"]/nlu, ph["glu_copy"]/nlu, ph["solve_spmv"]/nsolve, ph["f_flux"]/nfe, ph["f_gather"]/nfe))
-print("glu loop total per LU (io slot): %.0f" % (ph["io"]/nlu))
+print("glu loop total per LU (io slot): %.0f" % (ph["glu_loop"]/nlu))
 print("cycles per op: LU %.0f (head %.0f schur %.0f tail %.0f) solve %.0f f %.0f jac %.0f vec/step %.0f" % (
     (ph["fact_head"]+ph["fact_schur"]+ph["fact_tail"])/nlu, ph["fact_head"]/nlu, ph["fact_schur"]/nlu, ph["fact_tail"]/nlu,
     ph["solve"]/nsolve, ph["f"]/nfe, ph["jac"]/nje, ph["vec"]/nst))
