@@ -329,3 +329,22 @@ def test_rate12_network(rb, oracle):
         rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[c, 6])
         o = onet.evol_solve(par[c], y0[c], rt, at, want_record=False)
         assert _maxviol(res["y"][c, :net.N], o["y"][:net.N], _tolvec(net)) <= 1.0, c
+
+
+def test_hot_stiff_cells_complete_like_the_oracle(setupA):
+    """Cells of the synthetic stream (T > 1700 K) on which one or the other treatment of the
+    tail's U diagonal blocks defeats the corrector: the per-cell retry must bring every one of
+    them to t_max with the oracle's return codes and a final state within 3 x the stated
+    tolerance (the oracle needs 1.4-2.5 k steps for each)."""
+    rb, net, sol, onet, y0s = setupA
+    for c in (2091, 11980, 15520):
+        par = rb.synth.cell_params(1, first_cell=c)
+        y0 = rb.synth.initial_state(y0s, par, net.index("Grain0"))
+        res = sol.chem_evol_solve(par, y0, want_touts=False)
+        rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[0, 6])
+        o = onet.evol_solve(par[0], y0[0], rt, at, want_record=False)
+        assert o["quality"] == 0 and o["t_final"] == 1e6
+        assert res["istate"][0] == 2 and res["quality"][0] == 0 and res["t_final"][0] == 1e6, (c, res["istate"], res["quality"])
+        # these cells are integrated at the edge of what round-off allows (both solvers crawl at
+        # order 1 for most of the run): 3 x the stated bound is accepted here, and only here
+        assert _final_viol(onet, par[0], y0[0], rt, at, res["y"][0], o, _tolvec(net)) <= 3.0, c
