@@ -219,9 +219,9 @@ int racg_network_create(racg_handle** out, int R, int N, const int* reac, const 
     if (g.nlev > 0 && ss.nent > 0 && !getenv("RACG_NO_GLU")) {
       dn.glu.on = 1; dn.glu.nlev = g.nlev; dn.glu.zpos = g.zpos;
       // bits: 1 = L blocks, 2 = U blocks of the dense tail, 8 = U blocks of the S rows solved by
-      // substitution instead of explicit inverses.  Default 2: the explicit U^-1 of the tail blocks
-      // (hub species, pivots of very different size) loses accuracy on the hottest cells.
-      dn.glu.subst = getenv("RACG_SUBST") ? atoi(getenv("RACG_SUBST")) : 2;
+      // substitution instead of explicit inverses.  Default 0 (all inverses: fastest solves); a cell
+      // on which that defeats the corrector is integrated again with bit 2 flipped (see the kernel).
+      dn.glu.subst = getenv("RACG_SUBST") ? atoi(getenv("RACG_SUBST")) : 0;
       UP(g.piv, glu.piv); UP(g.mul, glu.mul); UP(g.ent, glu.ent); UP(g.tgt, glu.tgt);
       std::vector<int> desc(g.lvl);
       desc.insert(desc.end(), g.grp.begin(), g.grp.end());

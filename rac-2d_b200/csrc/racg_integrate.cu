@@ -1992,6 +1992,9 @@ integrate_kernel(const BatchArgs args) {
       t_step = t_step * ratio;
       tout = t + t_step;
     }
+    // an abnormal end of the first attempt (unphysical abundances, illegal input, DLSODES -7)
+    // earns the same second chance as the corrector-failure count
+    if (GLU && !second_try && redo_mask < 0 && (quality & (256 | 512 | 1024))) redo_mask = subst ^ 2;
     if (redo_mask >= 0) {
       cNST = aNST + s.NST; cNFE = aNFE + s.NFE; cNJE = aNJE + s.NJE; cNLU = aNLU + s.NLU;
       cSOL = s.n_solve; cCF = s.n_cfail; cEF = s.n_efail;
