@@ -167,6 +167,10 @@ int racg_solve_batch_dev(racg_handle* h, int ncell, const double* cellpar, const
  * x of (I + con*J) x = f(y) from the integrator's own factorisation and solve (con = -h*el0). */
 int racg_debug_fjac(racg_handle* h, int ncell, const double* cellpar, const double* y, double* f,
                     double* jstore, int* csc_to_store, int* nstore, double con);
+/* host-side consistency check of the level-parallel factorisation schedule and of the staged
+ * solves against the symbolic pattern (no GPU needed): 0 = consistent, RACG_ERR_NETWORK with a
+ * message otherwise */
+int racg_selfcheck(const racg_handle* h);
 /* number of kernel launches issued through this handle so far */
 long racg_launch_count(const racg_handle* h);
 /* per-phase SM-cycle counters of the last racg_solve_batch* call, summed over CTAs:

@@ -293,6 +293,10 @@ class ChemSolver:
         pd[:, m] = j_t[c2s[m], :].T
         return f_t.T.copy(), pd
 
+    def selfcheck(self):
+        """host-side consistency check of the factorisation / solve schedules (no GPU needed)"""
+        _check(lib().racg_selfcheck(self.h))
+
     def launch_count(self):
         return int(lib().racg_launch_count(self.h))
 

@@ -512,6 +512,13 @@ int racg_debug_fjac(racg_handle* h, int ncell, const double* cellpar, const doub
   return 0;
 }
 
+int racg_selfcheck(const racg_handle* h) {
+  if (!h) return fail(RACG_ERR_ARG, "null argument");
+  std::string err;
+  if (!selfcheck_schedules(h->hn, err)) return fail(RACG_ERR_NETWORK, "schedule self-check: " + err);
+  return 0;
+}
+
 long racg_launch_count(const racg_handle* h) { return h ? h->launches : 0; }
 
 int racg_phase_cycles(racg_handle* h, double* out) {

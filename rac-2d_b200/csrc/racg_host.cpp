@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <map>
 #include <numeric>
+#include <set>
 
 namespace racg {
 
@@ -783,6 +784,157 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     jc.ngroups = (int)jc.grp_accum.size();
     for (int k = 0; k < hn.NNZ; ++k) if (!written[k]) jc.zero_slots.push_back(k);
   }
+  return true;
+}
+
+bool selfcheck_schedules(const HostNet& hn, std::string& err) {
+  const HostNet::LevelLU& g = hn.glu;
+  const HostNet::SolveSched& ss = hn.ss;
+  if (g.nlev == 0) { err = "no level-parallel schedule for this network"; return false; }
+  const int nh = hn.nh, nt = hn.nt;
+  auto fail = [&](const std::string& m) { err = m; return false; };
+  // storage position of (i,j) in the permuted numbering, -1 if outside the pattern
+  auto pos = [&](int i, int j) -> int {
+    if (i >= nh && j >= nh) return hn.o_tl + (j - nh) * hn.ldt + (i - nh);
+    if (i < nh && j < nh) {
+      auto lo = hn.hh_col.begin() + hn.hh_ptr[i], hi = hn.hh_col.begin() + hn.hh_ptr[i + 1];
+      auto it = std::lower_bound(lo, hi, (uint16_t)j);
+      return (it == hi || *it != j) ? -1 : (int)(it - hn.hh_col.begin());
+    }
+    if (i < nh) {
+      auto lo = hn.ub_col.begin() + hn.ub_ptr[i], hi = hn.ub_col.begin() + hn.ub_ptr[i + 1];
+      auto it = std::lower_bound(lo, hi, (uint16_t)(j - nh));
+      return (it == hi || *it != j - nh) ? -1 : hn.o_ub + (int)(it - hn.ub_col.begin());
+    }
+    auto lo = hn.lc_col.begin() + hn.lc_ptr[i - nh], hi = hn.lc_col.begin() + hn.lc_ptr[i - nh + 1];
+    auto it = std::lower_bound(lo, hi, (uint16_t)j);
+    return (it == hi || *it != j) ? -1 : hn.o_lc + (int)(it - hn.lc_col.begin());
+  };
+  // rows below / columns right of every head pivot
+  std::vector<std::vector<int>> rows_of(nh), cols_of(nh);
+  for (int i = 0; i < nh; ++i) {
+    for (int q = hn.hh_ptr[i]; q < hn.hh_ptr[i] + hn.hh_nl[i]; ++q) rows_of[hn.hh_col[q]].push_back(i);
+    for (int q = hn.hh_ptr[i] + hn.hh_nl[i] + 1; q < hn.hh_ptr[i + 1]; ++q) cols_of[i].push_back(hn.hh_col[q]);
+    for (int q = hn.ub_ptr[i]; q < hn.ub_ptr[i + 1]; ++q) cols_of[i].push_back(nh + hn.ub_col[q]);
+    if (hn.hh_col[hn.hh_ptr[i] + hn.hh_nl[i]] != i) return fail("diagonal entry misplaced in a head row");
+  }
+  for (int a = 0; a < nt; ++a)
+    for (int q = hn.lc_ptr[a]; q < hn.lc_ptr[a + 1]; ++q) rows_of[hn.lc_col[q]].push_back(nh + a);
+  // level of every pivot from the schedule
+  std::vector<int> level_of(nh, -1);
+  for (int L = 0; L < g.nlev; ++L)
+    for (int q = g.lvl[4 * L]; q < g.lvl[4 * (L + 1)]; ++q) {
+      const int k = (int)(g.piv[q] >> 16);
+      if (k < 0 || k >= nh || level_of[k] >= 0) return fail("pivot listed twice or out of range");
+      if ((int)(g.piv[q] & 0xffff) != pos(k, k)) return fail("wrong diagonal position of a pivot");
+      level_of[k] = L;
+    }
+  for (int k = 0; k < nh; ++k) if (level_of[k] < 0) return fail("pivot missing from the level schedule");
+  long npairs = 0;
+  for (int L = 0; L < g.nlev; ++L) {
+    // expected work of the level
+    std::map<std::pair<int, int>, int> expect;            // (l position, u position) -> target
+    std::set<std::pair<int, int>> expect_mul;             // (position of a(i,k), diagonal position)
+    std::set<int> operands;
+    for (int k = 0; k < nh; ++k) {
+      if (level_of[k] != L) continue;
+      for (int i : rows_of[k]) {
+        const int pl = pos(i, k);
+        expect_mul.insert({pl, pos(k, k)});
+        operands.insert(pl);
+        for (int j : cols_of[k]) {
+          const int pu = pos(k, j), pt = pos(i, j);
+          if (pl < 0 || pu < 0 || pt < 0) return fail("update outside the symbolic pattern");
+          expect[{pl, pu}] = pt;
+          operands.insert(pu);
+        }
+      }
+    }
+    // multipliers
+    std::set<std::pair<int, int>> got_mul;
+    for (int q = g.lvl[4 * L + 1]; q < g.lvl[4 * (L + 1) + 1]; ++q)
+      if (!got_mul.insert({(int)(g.mul[q] & 0xffff), (int)(g.mul[q] >> 16)}).second) return fail("multiplier listed twice");
+    if (got_mul != expect_mul) return fail("multiplier list of a level differs from the pattern");
+    // updates
+    std::map<std::pair<int, int>, int> got;
+    std::set<int> targets;
+    const int r1 = g.lvl[4 * L + 3];
+    if (r1 >= 0) {
+      const int* A = &g.r1[8 * r1];
+      const int ua0 = A[0], nua4 = A[1], ub0 = A[2], tgt_off = A[4], nr = A[5], nj4 = A[6];
+      const int m0 = g.lvl[4 * L + 1];
+      for (int rc = 0; rc * 32 < nr; ++rc)
+        for (int j4 = 0; j4 < nj4; ++j4)
+          for (int l = 0; l < 32; ++l)
+            for (int c = 0; c < 4; ++c) {
+              const int t = g.r1tgt[((size_t)tgt_off + ((size_t)rc * nj4 + j4) * 32 + l) * 4 + c];
+              if (t == g.zpos + 1) continue;
+              const int m = rc * 32 + l;
+              if (m >= nr) return fail("rank-1 level: live target in an idle lane");
+              const int pl = (int)(g.mul[m0 + m] & 0xffff);
+              const int pu = (j4 < nua4) ? ua0 + 4 * j4 + c : ub0 + 4 * (j4 - nua4) + c;
+              if (!got.insert({{pl, pu}, t}).second) return fail("rank-1 level: update listed twice");
+              if (!targets.insert(t).second) return fail("rank-1 level: target written twice");
+            }
+    }
+    for (int gi = g.lvl[4 * L + 2]; gi < g.lvl[4 * (L + 1) + 2]; ++gi) {
+      const int width = g.grp[4 * gi], nblk = g.grp[4 * gi + 1], ent_off = g.grp[4 * gi + 2], tgt_off = g.grp[4 * gi + 3];
+      for (int b = 0; b < nblk; ++b)
+        for (int l = 0; l < 32; ++l) {
+          const int t = g.tgt[(size_t)tgt_off + b * 32 + l];
+          bool any = false;
+          for (int j = 0; j < width; ++j) {
+            const uint32_t e = g.ent[(size_t)ent_off + ((size_t)b * width + j) * 32 + l];
+            const int pl = (int)(e & 0xffff), pu = (int)(e >> 16);
+            if (pl == g.zpos && pu == g.zpos) continue;
+            if (t == 0xFFFF) return fail("live entry in an idle lane");
+            if (!got.insert({{pl, pu}, t}).second) return fail("update listed twice");
+            any = true;
+          }
+          if (any && !targets.insert(t).second) return fail("target written by two lanes of one level");
+        }
+    }
+    if (got != expect) return fail("updates of a level differ from the symbolic factorisation (level " + std::to_string(L) + ")");
+    for (int t : targets) if (operands.count(t)) return fail("a target of a level is also an operand of that level");
+    npairs += (long)got.size();
+  }
+  if (npairs != g.npairs) return fail("pair count mismatch");
+  // staged solves: every L / U entry of the head block exactly once (stage entry or S diagonal block)
+  std::vector<int> seenL(hn.n_hh, 0), seenU(hn.n_hh, 0);
+  const uint32_t* ent = ss.blob.data();
+  const uint16_t* rp = (const uint16_t*)(ent + ss.nent);
+  const uint16_t* rows = rp + ((ss.nrp + 1) & ~1);
+  const int nstage = (int)ss.st.size() / 4;
+  if (nstage != ss.nf + ss.nb) return fail("stage count mismatch");
+  std::vector<int> done_f(nh, 0), done_b(nh, 0);
+  for (int s = 0; s < nstage; ++s) {
+    const bool upper = s >= ss.nf;
+    const int kind = ss.st[4 * s] & 255, nrows = ss.st[4 * s + 1] & 0xffff, row_off = ss.st[4 * s + 2], rp_off = ss.st[4 * s + 3];
+    if ((kind == 1) != (upper && kind != 2) || (kind == 0 && upper)) return fail("stage kind does not match its sweep");
+    for (int r = 0; r < nrows; ++r) {
+      const int i = rows[row_off + r];
+      for (int q = rp[rp_off + r]; q < rp[rp_off + r + 1]; ++q) {
+        const int p = (int)(ent[q] & 0xffff), c = (int)(ent[q] >> 16);
+        if (p < hn.hh_ptr[i] || p >= hn.hh_ptr[i + 1] || hn.hh_col[p] != c) return fail("stage entry does not belong to its row");
+        if (upper ? (c <= i) : (c >= i)) return fail("stage entry on the wrong side of the diagonal");
+        // the operand must already be solved: an earlier stage of the same sweep
+        if (!(upper ? done_b[c] : done_f[c]) && !(!upper && hn.hh_nl[c] == 0)) return fail("stage reads a row that is not solved yet");
+        (upper ? seenU : seenL)[p] += 1;
+      }
+    }
+    for (int r = 0; r < nrows; ++r) (upper ? done_b : done_f)[rows[row_off + r]] = 1;
+  }
+  for (uint32_t e : ss.ext) {
+    const int p = (int)(e & 0xffff);
+    if (p < 0 || p >= hn.n_hh) return fail("extraction entry outside the head block");
+    seenL[p] += 1; seenU[p] += 1;       // diagonal-block entries are handled by the block solve
+  }
+  for (int i = 0; i < nh; ++i)
+    for (int q = hn.hh_ptr[i]; q < hn.hh_ptr[i + 1]; ++q) {
+      const int c = hn.hh_col[q];
+      if (c < i && seenL[q] != 1) return fail("an L entry of the head block is not covered exactly once by the forward stages");
+      if (c > i && seenU[q] != 1) return fail("a U entry of the head block is not covered exactly once by the backward stages");
+    }
   return true;
 }
 

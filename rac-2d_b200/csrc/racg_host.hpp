@@ -158,4 +158,12 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
                     const double* mass_num, const double* vib_freq, const double* Edesorb,
                     const int* dupli_ptr, const int* dupli_list, const racg_cfg* cfg);
 
+// Host-side consistency check of the factorisation / solve schedules against the symbolic
+// pattern they were derived from (used by the CPU tests; returns false and a message on the
+// first inconsistency): every update a(i,j) -= l(i,k) u(k,j) of the head pivots appears exactly
+// once and in the level of its pivot, the targets of one level are distinct and never operands
+// of that level, every multiplier is listed once, and the staged solves cover every L and U
+// entry of the head block exactly once.
+bool selfcheck_schedules(const HostNet& hn, std::string& err);
+
 }  // namespace racg

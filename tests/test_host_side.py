@@ -40,6 +40,16 @@ def test_loader_and_pattern_bit_exact_vs_oracle(rb, oracle, path):
         assert np.array_equal(net.chem_load_initial_abundances(ic), o.load_initial_abundances(ic))
 
 
+@pytest.mark.parametrize("path", [NET_A, NET_B, NET_C])
+def test_factorisation_and_solve_schedules_are_consistent(rb, path):
+    """Every update of the symbolic LU appears exactly once and in the level of its pivot, the
+    targets of a level are distinct and never operands of that level, the staged solves cover
+    every L/U entry of the head block once (racg_selfcheck, host only)."""
+    net = rb.ChemNetwork(path)
+    sol = net.create_solver()
+    sol.selfcheck()
+
+
 def test_solver_flags_alt_matches_oracle(rb, oracle):
     net = rb.ChemNetwork(NET_A)
     o = oracle.Network(NET_A)
