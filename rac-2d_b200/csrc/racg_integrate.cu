@@ -12,14 +12,18 @@
 //   chem_cal_rates                  src/chemistry.f90:591-966
 // with YSMP's sparse LU replaced by a fixed-pattern LU on the host-computed ordering.
 //
-// Data placement (per cell):
+// Data placement (per cell), level-parallel mode (integrate_kernel<EPT, true>; networks whose
+// factor does not fit in 227 KB run the generic mode <EPT, false> with head rows in L2):
 //   registers      Nordsieck array YH (6 columns), ACOR, EWT, RTOL/ATOL: element i of every
 //                  vector lives in thread i mod 256 (all controller updates are elementwise)
-//   shared memory  y / savf / solve vector / 1/pivots, the dense "tail" block of the LU
-//                  (Schur complement of the hub species), the head x head block of the LU,
-//                  and a scratch region (reaction fluxes | factorisation work rows + U_B)
-//   L2-resident    per-CTA workspace: Jacobian in LU-slot order, ELL copies of the two
+//   shared memory  y / savf / solve vector / 1/pivots, the schedules' descriptors, and the
+//                  whole LU factor V in storage order [head x head | U_B | L_C | dense tail];
+//                  the U_B/L_C part is the scratch X between factorisations (fluxes, gather
+//                  partials, inverses of the S diagonal blocks, tables of the staged solves)
+//   L2-resident    per-CTA workspace: Jacobian in storage order, ELL copies of the two
 //                  coupling blocks U_B / L_C for the solves, the cell's rate coefficients
+// Factorisation: factor_glu (levels of independent pivots, gather schedules, rank-1 levels,
+// register-tiled dense tail, explicit block inverses); solves: solve_glu (staged sweeps).
 #include <cuda_runtime.h>
 #include <cstdio>
 #include "racg_dev.cuh"
@@ -32,7 +36,7 @@ constexpr int NW = NT / 32;       // warps per CTA
 constexpr int MAXTL = 8;          // tail tile edge per thread: nt <= 16 * MAXTL = 128
 
 enum Phase { PH_RATES = 0, PH_F, PH_JAC, PH_FACT_HEAD, PH_FACT_SCHUR, PH_FACT_TAIL, PH_SOLVE,
-             PH_VEC, PH_IO, PH_TOTAL, PH_NCELL, PH_PBUILD, PH_TAILINV, PH_S_FWD, PH_S_TAIL, PH_S_BWD,
+             PH_VEC, PH_G_LOOP, PH_TOTAL, PH_NCELL, PH_PBUILD, PH_TAILINV, PH_S_FWD, PH_S_TAIL, PH_S_BWD,
              PH_F_FLUX, PH_F_GATHER, PH_G_PIVMUL, PH_G_FLAT, PH_G_NARROW, PH_G_WIDE, PH_S_SPMV, PH_G_COPY, PH_COUNT };
 
 struct Smem {
@@ -750,7 +754,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
   for (int q = tid; q < net.n_ub; q += NT) ws.ubE[__ldg(net.ub_ellpos + q)] = V[net.o_ub + q];
   for (int q = tid; q < net.n_lc; q += NT) ws.lcE[__ldg(net.lc_ellpos + q)] = V[net.o_lc + q];
   __syncthreads();   // X (= the U_B/L_C part of V) is scratch from here on
-  if (tid == 0) { ph[PH_G_COPY] += clock64() - t1; ph[PH_IO] += t1 - t0b; }
+  if (tid == 0) { ph[PH_G_COPY] += clock64() - t1; ph[PH_G_LOOP] += t1 - t0b; }
   const long long t2 = clock64();
   // ---- tables of the staged solves and dense copies of the S diagonal blocks -> upper part of X
   {
