@@ -137,8 +137,8 @@ def test_synthetic_cells_deterministic_and_prefix_stable(rb):
 
 
 def test_world_size_2_sharding_with_gloo(tmp_path):
-    """N>1 path on CPU: each rank owns a contiguous block of the cell stream, results are
-    gathered with one all_gather; the union equals the single-rank batch."""
+    """N>1 path on CPU: the cell stream is dealt round-robin to the ranks (as bench.py does),
+    results are gathered with one all_gather; the union equals the single-rank batch."""
     script = tmp_path / "shard.py"
     script.write_text(f'''
 import os, sys
@@ -148,14 +148,14 @@ import rac2d_b200 as rb
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 ncell = 24
-par = rb.synth.cell_params(ncell, first_cell=rank * ncell)
+par = np.ascontiguousarray(rb.synth.cell_params(world * ncell)[rank::world])
 # stand-in for the solve: a deterministic per-cell function of the inputs
 yf = torch.from_numpy(np.ascontiguousarray(par[:, :8].T.copy()))
 out = torch.empty((world,) + tuple(yf.shape), dtype=yf.dtype)
 dist.all_gather_into_tensor(out.view(-1), yf.view(-1))
 full = rb.synth.cell_params(world * ncell)
 for r in range(world):
-    assert np.array_equal(out[r].numpy().T, full[r * ncell:(r + 1) * ncell, :8])
+    assert np.array_equal(out[r].numpy().T, full[r::world, :8])
 t = torch.tensor([float(rank + 1)], dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 assert t.item() == world
