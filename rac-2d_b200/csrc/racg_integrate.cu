@@ -1971,7 +1971,7 @@ integrate_kernel(const BatchArgs args) {
       record_out(irec);
       n_record_real = irec;
       if (GLU && !second_try && s.n_cfail > 4000) { redo_mask = subst ^ 2; break; }
-      if (aNST + s.NST > 500000) break;   // runaway guard: 5x the heaviest cell that completes normally
+      if (aNST + s.NST > 250000) break;   // runaway guard: 2.4x the heaviest cell that completes normally
       if (t >= t_max) break;
       if (ISTATE < 0) {
         NERR += 1; nerr_c += 1;
