@@ -605,6 +605,12 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     }
     g.lvl.insert(g.lvl.end(), {(int)g.piv.size(), (int)g.mul.size(), (int)g.grp.size() / 4, 0});
     if (!ok) g = HostNet::LevelLU();
+    // test hook (tests/test_host_side.py): damage one update so that the self-check must object
+    if (ok && getenv("RACG_TEST_CORRUPT_SCHEDULE") && !g.ent.empty()) {
+      const int mode = atoi(getenv("RACG_TEST_CORRUPT_SCHEDULE"));
+      if (mode == 1) g.ent[g.ent.size() / 2] ^= 1u;                       // wrong operand position
+      else if (mode == 2 && g.r1tgt.size() > 8) g.r1tgt[5] = g.r1tgt[4];  // target written twice
+    }
     if (ok) {
       HostNet::SolveSched& ss = hn.ss;
       // S: the longest suffix of levels holding <= 96 rows

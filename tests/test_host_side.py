@@ -50,6 +50,32 @@ def test_factorisation_and_solve_schedules_are_consistent(rb, path):
     sol.selfcheck()
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_schedule_selfcheck_detects_damage(mode):
+    """The self-check is not vacuous: a schedule with one damaged entry is rejected."""
+    code = ("import sys; sys.path.insert(0, %r); import rac2d_b200 as rb\n"
+            "net = rb.ChemNetwork(%r); sol = net.create_solver()\n"
+            "try:\n    sol.selfcheck(); print('ACCEPTED')\n"
+            "except rb.RacgError as e:\n    print('REJECTED', e)\n") % (ROOT, NET_A)
+    env = dict(os.environ, RACG_TEST_CORRUPT_SCHEDULE=mode)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert "REJECTED" in out.stdout and "self-check" in out.stdout, out.stdout + out.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU arm) prints one JSON line with the contract's keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-cells", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "cells/s" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+
+
 def test_solver_flags_alt_matches_oracle(rb, oracle):
     net = rb.ChemNetwork(NET_A)
     o = oracle.Network(NET_A)
