@@ -288,7 +288,10 @@ jac_kernel4(const DevNet net, const JacColTables jc, int ncell, const double* __
       for (int s = sb + w; s < se; s += NWARP) {
         const int slot = __ldg(jc.slot_id + s), e0 = __ldg(jc.slot_ent_ptr + s), e1 = __ldg(jc.slot_ent_ptr + s + 1);
         double* op = pd + (size_t)slot * ncell + cell;
-        D4 acc = ld4(op, accum && ok);
+        // coherent read (not the read-only path): an earlier group of this kernel stored the value
+        D4 acc;
+        if (accum && ok) { const double2 a = __ldcg((const double2*)op), b2 = __ldcg((const double2*)op + 1); acc.v[0] = a.x; acc.v[1] = a.y; acc.v[2] = b2.x; acc.v[3] = b2.y; }
+        else { acc.v[0] = acc.v[1] = acc.v[2] = acc.v[3] = 0.0; }
         for (int e = e0; e < e1; ++e) {
           const uint32_t v = __ldg(jc.ent + e);
           const double cf = (double)((int)(v >> 24) - 4);
