@@ -14,8 +14,13 @@
  * index VALUES are 1-based exactly as in the reference tables; scalars by value.
  * Every function returns 0 on success and a negative code on error (never
  * aborts, never falls back to a CPU path); racg_last_error() gives the text.
- * A handle is bound to the CUDA device current at creation; use one handle per
- * host thread / per GPU.
+ * A handle is created on the CUDA device current at creation and can be replicated
+ * to more GPUs of the node with racg_use_devices(); every compute entry point selects
+ * the handle's device(s) itself and restores the caller's device on return.  No state
+ * is shared between handles (each owns its tables, workspace, stream and constant-memory
+ * slot); calls on ONE handle must not overlap (one host thread per handle, and for the
+ * *_dev variants one stream per handle, in stream order).  The library reads no
+ * environment variables.
  */
 #ifndef RACG_H
 #define RACG_H
@@ -99,6 +104,23 @@ int racg_network_create(racg_handle** h, int R, int N, const int* reac, const in
                         const int* dupli_list, const racg_cfg* cfg);
 int racg_destroy(racg_handle* h);
 
+/* Multi-GPU (north_star (e): cells are independent, shards never exchange data): replicate the
+ * network tables and workspaces on the listed CUDA devices (ndev <= 0: every visible device).
+ * Afterwards the host-pointer racg_solve_batch deals the cells of a batch to these devices
+ * (by descending cost of the previous batch of the same size, else round-robin), runs the
+ * shards concurrently from the calling thread and gathers the results into the caller's arrays.
+ * This is what the serial cell loop of the Fortran host (src/disk.f90:864-938) needs to use
+ * all GPUs of a node through one call.  The *_dev variants always run on the first device. */
+int racg_use_devices(racg_handle* h, int ndev, const int* devices);
+int racg_device_count(const racg_handle* h);
+/* options: "warm_order" (default 1: a batch with as many cells as the previous one is queued
+ * heaviest-first from that batch's per-cell cost; order only, results do not depend on it),
+ * "level_lu" (default 1; 0 forces the generic factorisation path, diagnostics),
+ * "block_mode" (diagnostics: how diagonal blocks of the triangular solves are treated) */
+int racg_set_option(racg_handle* h, const char* name, double value);
+/* human-readable summary of the shared symbolic factorisation and schedules */
+int racg_network_describe(const racg_handle* h, char* buf, int len);
+
 /* sizes[0..7] = R, N, NEQ, NNZ (= chemsol_params%NNZ), NNZ after DPREP's diagonals,
  * nnz(L+D+U) of the shared symbolic factorisation (species block), dense-tail size,
  * number of factorisation levels */
@@ -127,20 +149,37 @@ typedef struct racg_solve_params {
   double ratio_tstep;        /* chemsol_params%ratio_tstep */
   int mxstep_per_interval;   /* IWORK(6) */
   int steps_reset_solver;    /* chemsol_params%steps_reset_solver */
-  int nrec_max;              /* leading capacity of touts/record per cell */
+  int nrec_max;              /* leading capacity of touts/record per cell (0 allowed when both are NULL);
+                                capacity only: every cell runs its own n_record
+                                (chem_evol_solve_prepare_run_once, src/chemistry.f90:1894-1899) and
+                                records beyond nrec_max are not stored */
   int tol_policy_j;          /* used when rtol/atol are NULL: chem_set_solver_flags_alt(j) */
   double RTOL, ATOL;         /* chemsol_params%RTOL/ATOL for the policy */
+  double max_runtime_allowed;/* chemsol_params%max_runtime_allowed (src/chemistry.f90:116, 438, 480-491)
+                                in MODEL seconds, <= 0: no budget.  The reference measures cpu_time; here
+                                the clock is the deterministic work model racg_model_runtime() so that the
+                                same cell is cut at the same place on every machine (and in the oracle). */
 } racg_solve_params;
+
+/* The deterministic stand-in for the reference's cpu_time clock (src/sub_trivials.f90:25-42):
+ * seconds = c_f*NFE + c_jac*NJE + c_lu*NLU + c_solve*n_solve + c_step*NST, constants = what the
+ * reference algorithm (O(NEQ*R) Jacobian, scalar sparse LDU) costs per operation on one host core
+ * per unit of network size.  coef[5] receives c_f, c_jac, c_lu, c_solve, c_step
+ * for this network. */
+int racg_model_runtime_coefs(const racg_handle* h, double* coef);
 
 /* The batch replacement for the loop body around `call chem_evol_solve`
  * (src/disk.f90:1686; semantics of src/chemistry.f90:391-588 with evolT=.false.
- * and the cpu_time budgets replaced by the MXSTEP budget).
+ * and the cpu_time budgets replaced by the deterministic work model, see max_runtime_allowed).
  *   in : cellpar(ncell,NPAR), y0(ncell,NEQ) [y0(:,NEQ) = Tgas], t0/tmax/dt_first(ncell),
  *        rtol/atol(ncell,NEQ) or NULL (policy j)
  *   out: y_final(ncell,NEQ), t_final(ncell), nrec_real(ncell), istate(ncell)
  *        [DLSODES codes: 2 ok, -1..-7], quality(ncell) [bits 1,2,256,512 as
- *        src/chemistry.f90:506,528,577-582], stats(ncell,RACG_NSTAT) =
- *        NST,NFE,NJE,NLU,NQU,n_solve,NERR,n_restart,n_cfail,n_efail,nrec_real,istate,HU,..
+ *        src/chemistry.f90:506,528,577-582; bit 1024 = DLSODES returned -7 (sparse-solver
+ *        failure), where the reference calls error_stop (src/chemistry.f90:375-380)],
+ *        stats(ncell,RACG_NSTAT) =
+ *        NST,NFE,NJE,NLU,NQU,n_solve,NERR,n_restart,n_cfail,n_efail,nrec_real,istate,HU,
+ *        model runtime [s], premature-finish flag (1 = the work budget ended the cell), 0
  *        touts(ncell,nrec_max), record(ncell,NEQ,nrec_max): optional (NULL to skip). */
 int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const double* y0,
                      const double* rtol, const double* atol, const double* t0,
@@ -171,6 +210,9 @@ int racg_debug_fjac(racg_handle* h, int ncell, const double* cellpar, const doub
  * solves against the symbolic pattern (no GPU needed): 0 = consistent, RACG_ERR_NETWORK with a
  * message otherwise */
 int racg_selfcheck(const racg_handle* h);
+/* the same check on a copy of the schedules damaged on purpose (mode 1: one operand position
+ * flipped, 2: one target written twice): must return RACG_ERR_NETWORK (test of the checker) */
+int racg_selfcheck_damaged(const racg_handle* h, int mode);
 /* number of kernel launches issued through this handle so far */
 long racg_launch_count(const racg_handle* h);
 /* per-phase SM-cycle counters of the last racg_solve_batch* call, summed over CTAs:

@@ -113,7 +113,17 @@ typedef struct raco_solve_opts {
   int mxstep_per_interval;   /* IWORK(6) */
   int steps_reset_solver;
   int n_record;              /* capacity of touts/record (>= computed n_record) */
+  double max_runtime_allowed; /* chemsol_params%max_runtime_allowed (src/chemistry.f90:116) in MODEL
+                                 seconds (raco_model_runtime_coefs), <= 0: budgets disabled */
 } raco_solve_opts;
+
+/* Deterministic stand-in for the reference's cpu_time clock (src/sub_trivials.f90:25-42;
+ * used by src/chemistry.f90:438, 480-491): seconds = c_f*NFE + c_jac*NJE + c_lu*NLU +
+ * c_solve*n_solve + c_step*NST with per-operation costs of the reference algorithm on one
+ * host core, scaled by network size: c_f = 1.04e-8*R, c_jac = 6.45e-9*NEQ*R (column-wise
+ * chem_ode_jac), c_lu = 1.41e-7*NNZ, c_solve = 3.0e-9*NNZ, c_step = 6.4e-8*NEQ (fitted to this
+ * oracle, jac_mode = 1, -O2, 300 cells of the config-2 stream).  coef[5]. */
+void raco_model_runtime_coefs(int R, int NEQ, int NNZ, double* coef);
 
 /* stats[0..15]: NST,NFE,NJE,NLU,NQU(last),n_solve,n_err,n_restart,n_cfail,n_efail,
  *               n_record_real, last istate, ... accumulated over the whole cell */

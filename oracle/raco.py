@@ -31,7 +31,8 @@ class Cfg(C.Structure):
 class SolveOpts(C.Structure):
     _fields_ = [("t0", C.c_double), ("t_max", C.c_double), ("dt_first_step", C.c_double),
                 ("ratio_tstep", C.c_double), ("mxstep_per_interval", C.c_int),
-                ("steps_reset_solver", C.c_int), ("n_record", C.c_int)]
+                ("steps_reset_solver", C.c_int), ("n_record", C.c_int),
+                ("max_runtime_allowed", C.c_double)]
 
 
 def build(force=False):
@@ -173,11 +174,11 @@ class Network:
         return rt, at
 
     def evol_solve(self, par, y, rtols, atols, t0=0.0, t_max=1e6, dt_first_step=1e-8, ratio=1.1,
-                   mxstep=6000, steps_reset=50, cfg=None, want_record=True):
+                   mxstep=6000, steps_reset=50, cfg=None, want_record=True, max_runtime_allowed=0.0):
         """chem_evol_solve for one cell. Returns dict(y, touts, record, t_final, ...)."""
         cfg = cfg or default_cfg()
         nrec = lib().raco_n_record(t0, t_max, dt_first_step, ratio)
-        o = SolveOpts(t0, t_max, dt_first_step, ratio, mxstep, steps_reset, nrec)
+        o = SolveOpts(t0, t_max, dt_first_step, ratio, mxstep, steps_reset, nrec, max_runtime_allowed)
         y = np.array(y, np.float64)
         rt = np.array(rtols, np.float64)
         at = np.array(atols, np.float64)
@@ -198,14 +199,14 @@ class Network:
 
     def evol_solve_batch(self, par, y0, tol_j=1, RTOL=1e-4, ATOL=1e-30, t0=0.0, t_max=1e6,
                          dt_first_step=1e-8, ratio=1.1, mxstep=6000, steps_reset=50, nthreads=1,
-                         cfg=None):
+                         cfg=None, max_runtime_allowed=0.0):
         """par[ncell,NPAR], y0[ncell,NEQ] (cell-major). CPU baseline."""
         cfg = cfg or default_cfg()
         par = np.ascontiguousarray(par, np.float64)
         y0 = np.ascontiguousarray(y0, np.float64)
         ncell = par.shape[0]
         nrec = lib().raco_n_record(t0, t_max, dt_first_step, ratio)
-        o = SolveOpts(t0, t_max, dt_first_step, ratio, mxstep, steps_reset, nrec)
+        o = SolveOpts(t0, t_max, dt_first_step, ratio, mxstep, steps_reset, nrec, max_runtime_allowed)
         yf = np.zeros((ncell, self.NEQ))
         tf = np.zeros(ncell)
         ist = np.zeros(ncell, np.int32)

@@ -1,8 +1,9 @@
 // raco_solve.cpp -- ORACLE (test infrastructure only, see raco.h): the per-cell
 // output-time loop chem_evol_solve (src/chemistry.f90:391-588) with the error
-// policy ode_solver_error_handling (272-387), for evolT = .false. and with the
-// cpu_time budgets (438, 480-491) disabled (they make the reference
-// non-deterministic).
+// policy ode_solver_error_handling (272-387), for evolT = .false.  The cpu_time
+// budgets (438, 480-491) make the reference non-deterministic: here the
+// clock is a deterministic work model (raco_model_runtime_coefs) and the budget logic
+// itself is restated literally; max_runtime_allowed <= 0 disables it.
 #include "raco_internal.hpp"
 #include <thread>
 #include <atomic>
@@ -11,6 +12,14 @@
 using namespace raco;
 
 extern "C" {
+
+void raco_model_runtime_coefs(int R, int NEQ, int NNZ, double* coef) {
+  coef[0] = 1.04e-8 * R;
+  coef[1] = 6.45e-9 * (double)NEQ * R;
+  coef[2] = 1.41e-7 * NNZ;
+  coef[3] = 3.0e-9 * NNZ;
+  coef[4] = 6.4e-8 * NEQ;
+}
 
 int raco_n_record(double t0, double t_max, double dt_first_step, double ratio) {
   // src/chemistry.f90:1894-1899
@@ -38,6 +47,13 @@ int raco_evol_solve(const raco_net* h, const raco_cfg* cfg, const double* par,
 
   int n_record = raco_n_record(o->t0, o->t_max, o->dt_first_step, o->ratio_tstep);
   if (n_record > o->n_record) n_record = o->n_record;
+  // src/chemistry.f90:428-438: timer, runtime_laststep = huge, max_time_per_step
+  double coef[5];
+  raco_model_runtime_coefs(n.R, NEQ, n.NNZ, coef);
+  const bool budget = o->max_runtime_allowed > 0.0;
+  const double max_time_per_step = 5.0 / (double)n_record * o->max_runtime_allowed;
+  double time_laststep = 0.0, runtime_laststep = 1.7976931348623157e308;
+  bool premature = false;
   double t = o->t0;
   double t_step = o->dt_first_step;
   double tout = t + t_step;
@@ -61,6 +77,17 @@ int raco_evol_solve(const raco_net* h, const raco_cfg* cfg, const double* par,
     touts[i - 1] = t;
     if (record) for (int k = 0; k < NEQ; ++k) record[(size_t)(i - 1) * NEQ + k] = y[k];
     n_record_real = i;
+    if (budget) {   // src/chemistry.f90:480-494
+      harvest();
+      const double time_thisstep = coef[0] * (double)NFE + coef[1] * (double)NJE + coef[2] * (double)NLU +
+                                   coef[3] * (double)s.n_solve + coef[4] * (double)NST;
+      const double runtime_thisstep = time_thisstep - time_laststep;
+      if (runtime_thisstep > std::max(10.0 * runtime_laststep, 0.5 * o->max_runtime_allowed) ||
+          time_thisstep > o->max_runtime_allowed) { premature = true; break; }   // 'Premature finish'
+      if (runtime_thisstep > max_time_per_step) ISTATE = 1;
+      time_laststep = time_thisstep;
+      runtime_laststep = runtime_thisstep;
+    }
     if (t >= o->t_max) break;
     if (ISTATE < 0) {
       NERR += 1;
@@ -108,6 +135,9 @@ int raco_evol_solve(const raco_net* h, const raco_cfg* cfg, const double* par,
     stats[4] = s.NQU; stats[5] = (double)s.n_solve; stats[6] = NERR; stats[7] = (double)nrestart;
     stats[8] = (double)s.n_cfail; stats[9] = (double)s.n_efail; stats[10] = n_record_real;
     stats[11] = ISTATE; stats[12] = s.HU;
+    stats[13] = coef[0] * (double)NFE + coef[1] * (double)NJE + coef[2] * (double)NLU +
+                coef[3] * (double)s.n_solve + coef[4] * (double)NST;
+    stats[14] = premature ? 1.0 : 0.0;
   }
   return 0;
 }

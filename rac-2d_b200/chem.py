@@ -38,7 +38,7 @@ class Cfg(C.Structure):
 class SolveParams(C.Structure):
     _fields_ = [("ratio_tstep", C.c_double), ("mxstep_per_interval", C.c_int),
                 ("steps_reset_solver", C.c_int), ("nrec_max", C.c_int), ("tol_policy_j", C.c_int),
-                ("RTOL", C.c_double), ("ATOL", C.c_double)]
+                ("RTOL", C.c_double), ("ATOL", C.c_double), ("max_runtime_allowed", C.c_double)]
 
 
 def lib_path():
@@ -180,6 +180,30 @@ class ChemSolver:
             lib().racg_destroy(self.h)
             self.h = C.c_void_p()
 
+    # ---- devices and options --------------------------------------------
+    def use_devices(self, devices=None):
+        """Replicate the network on more GPUs of the node (None: every visible one); the
+        host-pointer chem_evol_solve then shards every batch over them."""
+        if devices is None:
+            _check(lib().racg_use_devices(self.h, C.c_int(0), None))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(lib().racg_use_devices(self.h, C.c_int(len(devices)), arr))
+        return int(lib().racg_device_count(self.h))
+
+    def set_option(self, name, value):
+        _check(lib().racg_set_option(self.h, name.encode(), C.c_double(value)))
+
+    def describe(self):
+        buf = C.create_string_buffer(8192)
+        _check(lib().racg_network_describe(self.h, buf, C.c_int(8192)))
+        return buf.value.decode()
+
+    def model_runtime_coefs(self):
+        c = np.zeros(5)
+        _check(lib().racg_model_runtime_coefs(self.h, _p(c)))
+        return c
+
     def __del__(self):
         try:
             self.close()
@@ -231,7 +255,7 @@ class ChemSolver:
     def chem_evol_solve(self, cellpar, y0, rtol=None, atol=None, t0=0.0, t_max=1e6,
                         dt_first_step=1e-8, ratio_tstep=1.1, mxstep_per_interval=6000,
                         steps_reset_solver=50, tol_policy_j=1, RTOL=1e-4, ATOL=1e-30,
-                        want_record=False, want_touts=True):
+                        want_record=False, want_touts=True, max_runtime_allowed=0.0, nrec_max=None):
         """The batch replacement of the loop body around `call chem_evol_solve`
         (src/disk.f90:1686).  Scalars t0/t_max/dt_first_step may be per-cell arrays."""
         par, y0 = _f(cellpar), _f(y0)
@@ -241,13 +265,16 @@ class ChemSolver:
         dta = np.ascontiguousarray(np.broadcast_to(np.asarray(dt_first_step, np.float64), (ncell,)))
         nrec = max([self.n_record(a, b, c, ratio_tstep) for a, b, c in
                     set(zip(t0a.tolist(), tma.tolist(), dta.tolist()))] or [2])
-        sp = SolveParams(ratio_tstep, mxstep_per_interval, steps_reset_solver, nrec, tol_policy_j, RTOL, ATOL)
+        if nrec_max is not None:
+            nrec = nrec_max
+        sp = SolveParams(ratio_tstep, mxstep_per_interval, steps_reset_solver, nrec, tol_policy_j, RTOL, ATOL,
+                         max_runtime_allowed)
         rt = _f(rtol) if rtol is not None else None
         at = _f(atol) if atol is not None else None
         yf = np.zeros((ncell, self.NEQ), order="F")
         tf = np.zeros(ncell)
-        touts = np.zeros((ncell, nrec), order="F") if want_touts else None
-        rec = np.zeros((ncell, self.NEQ, nrec), order="F") if want_record else None
+        touts = np.zeros((ncell, max(nrec, 1)), order="F") if want_touts else None
+        rec = np.zeros((ncell, self.NEQ, max(nrec, 1)), order="F") if want_record else None
         nrr = np.zeros(ncell, np.int32)
         ist = np.zeros(ncell, np.int32)
         q = np.zeros(ncell, np.int32)
@@ -296,6 +323,10 @@ class ChemSolver:
     def selfcheck(self):
         """host-side consistency check of the factorisation / solve schedules (no GPU needed)"""
         _check(lib().racg_selfcheck(self.h))
+
+    def selfcheck_damaged(self, mode):
+        """the same check on a deliberately damaged copy of the schedules: must raise"""
+        _check(lib().racg_selfcheck_damaged(self.h, C.c_int(mode)))
 
     def launch_count(self):
         return int(lib().racg_launch_count(self.h))

@@ -4,6 +4,8 @@
 #include <vector_types.h>
 #include "../../include/racg.h"
 
+#define RACG_MAX_NETS 8   // constant-memory slots = live handles per device (racg_integrate.cu)
+
 namespace racg {
 
 struct GatherDev {
@@ -89,10 +91,13 @@ struct DevNet {
   // BDF coefficients (DCFODE, METH=2): el[q][1..6], tesco[q][1..3], q = 1..5
   double el[6][8];
   double tesco[6][4];
+  // deterministic work model (include/racg.h racg_model_runtime_coefs): c_f, c_jac, c_lu, c_solve, c_step
+  double rt_coef[5];
 };
 
 struct BatchArgs {
   int ncell;
+  int net_slot;              // constant-memory slot of the handle's DevNet
   const double* cellpar;     // [NPAR][ncell]
   const double* y0;          // [NEQ][ncell]
   const double* rtol;        // [NEQ][ncell] or null

@@ -75,8 +75,10 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
                     const int* n_prod, const int* itype, const double* ABC, const double* T_range,
                     const char* ctype, const char* names, const int* elements,
                     const double* mass_num, const double* vib_freq, const double* Edesorb,
-                    const int* dupli_ptr, const int* dupli_list, const racg_cfg* cfg) {
+                    const int* dupli_ptr, const int* dupli_list, const racg_cfg* cfg, int nthreads) {
   if (R <= 0 || N <= 0 || N > 1000) { hn.error = "bad R/N (N must be <= 1000)"; return false; }
+  if (nthreads < 64 || (nthreads & (nthreads - 1))) { hn.error = "integrator thread count must be a power of two >= 64"; return false; }
+  hn.nthreads = nthreads;
   hn.R = R; hn.N = N; hn.NEQ = N + 1; hn.n = N;
   hn.cfg = *cfg;
   if (cfg->H2_form_use_moeq || cfg->update_gH_params_realtime || cfg->evol_dust_size) {
@@ -312,11 +314,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   if (clique_start < 0) clique_start = n - 1;
   int nt0 = ((n - clique_start + 15) / 16) * 16;
   nt0 = std::max(16, std::min(std::min(nt0, 128), (n / 16) * 16));
-  // tuning overrides (diagnostics only): RACG_NT = dense-tail size, RACG_MULTI = ratio of
-  // the multiple-elimination rounds
-  double multi_ratio = 1.0;
-  if (const char* e = getenv("RACG_NT")) nt0 = std::max(16, std::min((atoi(e) / 16) * 16, (n / 16) * 16));
-  if (const char* e = getenv("RACG_MULTI")) multi_ratio = atof(e);
+  const double multi_ratio = 1.0;   // ratio of the multiple-elimination rounds (1 = plain minimum degree)
   std::vector<uint64_t> F;
   const size_t smem_budget = 227 * 1024 - 2048;
   bool placed = false;
@@ -605,12 +603,6 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     }
     g.lvl.insert(g.lvl.end(), {(int)g.piv.size(), (int)g.mul.size(), (int)g.grp.size() / 4, 0});
     if (!ok) g = HostNet::LevelLU();
-    // test hook (tests/test_host_side.py): damage one update so that the self-check must object
-    if (ok && getenv("RACG_TEST_CORRUPT_SCHEDULE") && !g.ent.empty()) {
-      const int mode = atoi(getenv("RACG_TEST_CORRUPT_SCHEDULE"));
-      if (mode == 1) g.ent[g.ent.size() / 2] ^= 1u;                       // wrong operand position
-      else if (mode == 2 && g.r1tgt.size() > 8) g.r1tgt[5] = g.r1tgt[4];  // target written twice
-    }
     if (ok) {
       HostNet::SolveSched& ss = hn.ss;
       // S: the longest suffix of levels holding <= 96 rows
@@ -626,8 +618,10 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
         int maxlen = 0;
         for (auto& e : ents) maxlen = std::max(maxlen, (int)e.size());
         int lg;
-        if (kind == 2) lg = 3;
-        else { lg = 5; while (lg > 0 && (nrows << lg) > 256) --lg; while (lg > 0 && (1 << (lg - 1)) >= std::max(1, maxlen)) --lg; }
+        int lgblk = 0;
+        while ((32 << (lgblk + 1)) <= hn.nthreads) ++lgblk;      // lanes per row of a 32-row block stage
+        if (kind == 2) lg = lgblk;
+        else { lg = 5; while (lg > 0 && (nrows << lg) > hn.nthreads) --lg; while (lg > 0 && (1 << (lg - 1)) >= std::max(1, maxlen)) --lg; }
         const int row_off = (int)t_rows.size(), rp_off = (int)t_rp.size();
         for (int r = 0; r < nrows; ++r) {
           t_rows.push_back((uint16_t)rows[r]);
@@ -649,8 +643,9 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
         return e;
       };
       auto add_level = [&](int kind, const std::vector<int>& rows, bool upper) {
-        for (size_t r0 = 0; r0 < rows.size(); r0 += 256) {
-          std::vector<int> rr(rows.begin() + r0, rows.begin() + std::min(rows.size(), r0 + 256));
+        const size_t NTH = (size_t)hn.nthreads;
+        for (size_t r0 = 0; r0 < rows.size(); r0 += NTH) {
+          std::vector<int> rr(rows.begin() + r0, rows.begin() + std::min(rows.size(), r0 + NTH));
           std::vector<std::vector<uint32_t>> ee;
           for (int i : rr) ee.push_back(row_entries(i, upper, -1));
           add_stage(kind, rr, ee, 0);
@@ -705,24 +700,11 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
       }
     }
   }
-  if (getenv("RACG_VERBOSE")) {
-    fprintf(stderr, "racg: n=%d nh=%d nt=%d n_hh=%d n_ub=%d n_lc=%d nstore=%d nnz_lu=%d flev=%d su=%d | glu: nlev=%d "
-            "pairs=%ld ent=%zu mul=%zu groups=%zu | solve stages fwd=%d bwd=%d blocksS=%d ent=%d blob=%zu words | "
-            "ELL blocks U_B %d L_C %d:", n, nh, nt,
-            hn.n_hh, hn.n_ub, hn.n_lc, hn.nstore, hn.nnz_lu, (int)hn.flev_ptr.size() - 1,
-            (int)hn.su_ptr.size() - 1, hn.glu.nlev, hn.glu.npairs, hn.glu.ent.size(), hn.glu.mul.size(),
-            hn.glu.grp.size() / 4, hn.ss.nf, hn.ss.nb, hn.ss.nblkS, hn.ss.nent, hn.ss.blob.size(), hn.ubE.nblk, hn.lcE.nblk);
-    for (size_t q = 0; q < hn.ss.st.size(); q += 4)
-      fprintf(stderr, " [k%d lpr%d r%d]", hn.ss.st[q] & 255, 1 << ((hn.ss.st[q] >> 8) & 255), hn.ss.st[q + 1] & 0xffff);
-    fprintf(stderr, "\nracg: rank-1 levels %zu, target slots %zu; (nr,nc) per level:", hn.glu.r1.size() / 8, hn.glu.r1tgt.size());
-    for (size_t q = 0; q < hn.glu.r1.size(); q += 8) fprintf(stderr, " (%d,%d)", hn.glu.r1[q + 5], 4 * hn.glu.r1[q + 6]);
-    fprintf(stderr, "\n");
-  }
   // ---- stand-alone K3 schedule: columns grouped so that a group's partial
   // derivatives fit the shared-memory buffer; hub columns are cut into chunks that
   // accumulate into pd.
   {
-    const int CAP = getenv("RACG_JAC_CAP") ? atoi(getenv("RACG_JAC_CAP")) : 192;
+    const int CAP = 192;
     HostNet::JacCols& jc = hn.jc;
     std::vector<std::vector<uint32_t>> col_pairs(NEQ);
     for (int i = 0; i < R; ++i) {
@@ -791,6 +773,26 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     for (int k = 0; k < hn.NNZ; ++k) if (!written[k]) jc.zero_slots.push_back(k);
   }
   return true;
+}
+
+std::string describe_host_net(const HostNet& hn) {
+  char buf[4096];
+  int o = snprintf(buf, sizeof(buf),
+                   "n=%d nh=%d nt=%d n_hh=%d n_ub=%d n_lc=%d nstore=%d nnz_lu=%d flev=%d su=%d\n"
+                   "level LU: nlev=%d pairs=%ld ent=%zu mul=%zu groups=%zu rank1=%zu (target slots %zu)\n"
+                   "solve stages fwd=%d bwd=%d blocksS=%d ent=%d blob=%zu words; ELL blocks U_B %d L_C %d\nstages:",
+                   hn.n, hn.nh, hn.nt, hn.n_hh, hn.n_ub, hn.n_lc, hn.nstore, hn.nnz_lu, (int)hn.flev_ptr.size() - 1,
+                   (int)hn.su_ptr.size() - 1, hn.glu.nlev, hn.glu.npairs, hn.glu.ent.size(), hn.glu.mul.size(),
+                   hn.glu.grp.size() / 4, hn.glu.r1.size() / 8, hn.glu.r1tgt.size(), hn.ss.nf, hn.ss.nb, hn.ss.nblkS,
+                   hn.ss.nent, hn.ss.blob.size(), hn.ubE.nblk, hn.lcE.nblk);
+  for (size_t q = 0; q < hn.ss.st.size() && o < (int)sizeof(buf) - 64; q += 4)
+    o += snprintf(buf + o, sizeof(buf) - o, " [k%d lpr%d r%d]", hn.ss.st[q] & 255, 1 << ((hn.ss.st[q] >> 8) & 255),
+                  hn.ss.st[q + 1] & 0xffff);
+  if (o < (int)sizeof(buf) - 64) o += snprintf(buf + o, sizeof(buf) - o, "\nrank-1 levels (rows,cols):");
+  for (size_t q = 0; q < hn.glu.r1.size() && o < (int)sizeof(buf) - 64; q += 8)
+    o += snprintf(buf + o, sizeof(buf) - o, " (%d,%d)", hn.glu.r1[q + 5], 4 * hn.glu.r1[q + 6]);
+  snprintf(buf + o, sizeof(buf) - o, "\n");
+  return std::string(buf);
 }
 
 bool selfcheck_schedules(const HostNet& hn, std::string& err) {

@@ -41,6 +41,7 @@ struct Gather {
 
 struct HostNet {
   int R = 0, N = 0, NEQ = 0, NNZ = 0, NNZ_diag = 0;
+  int nthreads = 256;             // threads per cell of the integrator the solve stages are laid out for
   racg_cfg cfg;
   // reference tables (1-based values kept)
   std::vector<int> reac, prod, n_reac, n_prod, itype;
@@ -124,7 +125,7 @@ struct HostNet {
   // ---- staged triangular solves of the head block (racg_integrate.cu solve_glu).  The last
   // <= 96 head rows (deepest levels: a nearly dense chain) form 32-row blocks S whose diagonal
   // blocks are inverted explicitly after every factorisation; everything else goes level by
-  // level.  A stage is one pass of 256 threads: row r = tid / lpr gathers
+  // level.  A stage is one pass of the CTA's threads: row r = tid / lpr gathers
   // sum V[pos] * x[col] over its entries (lane tid % lpr takes every lpr-th one); the tables
   // are small enough to live in shared memory between factorisations.
   struct SolveSched {
@@ -156,7 +157,8 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
                     const int* n_prod, const int* itype, const double* ABC, const double* T_range,
                     const char* ctype, const char* names, const int* elements,
                     const double* mass_num, const double* vib_freq, const double* Edesorb,
-                    const int* dupli_ptr, const int* dupli_list, const racg_cfg* cfg);
+                    const int* dupli_ptr, const int* dupli_list, const racg_cfg* cfg, int nthreads);
+std::string describe_host_net(const HostNet& hn);
 
 // Host-side consistency check of the factorisation / solve schedules against the symbolic
 // pattern they were derived from (used by the CPU tests; returns false and a message on the

@@ -73,9 +73,13 @@ struct Layout { int hh_smem, ub_smem, nwr, glu; size_t xdoubles, total, voff; };
 // that the compiler emits shared-space (LDS/STS) instead of generic accesses
 extern __shared__ __align__(16) double smem_raw[];
 
-// network descriptor in constant memory: every device function reads it through the
-// constant cache (passing the ~1 KB struct by reference would spill it to local memory)
-__constant__ DevNet c_net;
+// Network descriptors in constant memory: every device function reads its network through the
+// constant cache (passing the ~1 KB struct by reference would spill it to local memory).  One
+// slot per live handle of the device, written once by racg_network_create (upload_net_slot) and
+// never touched by a launch: handles with different networks, or on different streams, do not
+// share any constant state.  Device functions take the slot index `ns`.
+__constant__ DevNet c_nets[RACG_MAX_NETS];
+#define c_net (c_nets[ns])
 
 // Shared-memory plan.  Preferred: everything (head x head block, the factorisation's copy
 // of U_B) on chip AND the total under 196 KB, so that the SM keeps >= 60 KB of L1 for the
@@ -201,7 +205,7 @@ __device__ __forceinline__ void run_gather(const GatherDev& g, const double* src
 
 // flux of reaction r (branches of chem_ode_f, src/disk.f90:4583-4643)
 __device__ __forceinline__ double flux_of(uint32_t w, double k, const double* y,
-                                          double DS) {
+                                          double DS, int ns) {
   const int kind = (w >> 20) & 3;
   const double y1 = y[w & 1023];
   if (kind == FK_ONE) return k * y1;
@@ -223,7 +227,7 @@ __device__ __forceinline__ double flux_of(uint32_t w, double k, const double* y,
 // d flux / d y(r1) (which = 0) or d flux / d y(r2) (which = 1)
 // (branches of chem_ode_jac, src/disk.f90:4765-4866)
 __device__ __forceinline__ double dflux_of(uint32_t w, double k, const double* y,
-                                           double DS, int which) {
+                                           double DS, int which, int ns) {
   const int kind = (w >> 20) & 3;
   const int r1 = w & 1023, r2 = (w >> 10) & 1023;
   if (kind == FK_ONE) return which == 0 ? k : 0.0;
@@ -249,7 +253,7 @@ __device__ __forceinline__ double dflux_of(uint32_t w, double k, const double* y
 // chem_ode_f: savf = S * flux(k, y).  k streamed from the workspace (L2), fluxes in the
 // scratch region X (x_off = its offset in the shared-memory block); y = smem_raw[0..n),
 // savf = smem_raw[n..2n)
-__device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off, double DS, unsigned long long* ph) {
+__device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off, double DS, unsigned long long* ph, int ns) {
   const DevNet& net = c_net;
   const int R = net.R;
   double* const fx = smem_raw + x_off;
@@ -269,7 +273,7 @@ __device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off,
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int r = r0 + u * NT;
-      if (r < R) fx[r] = flux_of(ww[u], kk[u], yv, DS);
+      if (r < R) fx[r] = flux_of(ww[u], kk[u], yv, DS, ns);
     }
   }
   for (int i = threadIdx.x; i < net.n; i += NT) out[i] = 0.0;
@@ -280,14 +284,14 @@ __device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off,
 }
 
 // chem_ode_jac for all columns at once -> ws.J (two passes over the reactions)
-__device__ __forceinline__ void eval_jac(const double* __restrict__ ks, int x_off, double* J, double DS) {
+__device__ __forceinline__ void eval_jac(const double* __restrict__ ks, int x_off, double* J, double DS, int ns) {
   const DevNet& net = c_net;
   double* const dfx = smem_raw + x_off;
   double* const px = dfx + net.R;
   const double* const yv = smem_raw;
   __syncthreads();
   for (int pass = 0; pass < 2; ++pass) {
-    for (int r = threadIdx.x; r < net.R; r += NT) dfx[r] = dflux_of(__ldg(net.fw + r), __ldcg(ks + r), yv, DS, pass);
+    for (int r = threadIdx.x; r < net.R; r += NT) dfx[r] = dflux_of(__ldg(net.fw + r), __ldcg(ks + r), yv, DS, pass, ns);
     __syncthreads();
     run_gather<true>(net.jac[pass], dfx, J, px);
   }
@@ -337,7 +341,7 @@ __device__ __forceinline__ void tail_step(double (&t)[TL][TL], int k, int kr, in
 }
 
 template <int TL>
-__device__ __noinline__ void tail_lu(int dt_off, int pub_off, int* flag) {
+__device__ __noinline__ void tail_lu(int dt_off, int pub_off, int* flag, int ns) {
   const DevNet& net = c_net;
   const int nt = net.nt, ldt = net.ldt;
   double* const Dt = smem_raw + dt_off;     // offsets into the shared-memory block: keeps
@@ -374,7 +378,7 @@ __device__ __noinline__ void tail_lu(int dt_off, int pub_off, int* flag) {
 // Replace every diagonal 32x32 block of the factored tail by the inverses of its unit-lower
 // and upper triangles (in place), so that the tail substitution becomes a few mat-vecs.
 // One thread per (block, triangle, column), the column of the inverse in registers.
-__device__ __noinline__ void tail_block_inverses(Smem sm) {
+__device__ __noinline__ void tail_block_inverses(Smem sm, int ns) {
   const DevNet& net = c_net;
   const int nt = net.nt, ldt = net.ldt, nb = (nt + 31) >> 5;
   const int job = threadIdx.x >> 5, j = threadIdx.x & 31;     // job = 2*block + (0: L, 1: U)
@@ -431,7 +435,7 @@ __device__ __noinline__ void tail_block_inverses(Smem sm) {
 // Shared-memory view of the level-parallel mode, derived from the smem_raw symbol so that
 // every access below is a shared-space access.
 struct GSm { double *y, *xb, *dinv, *V, *X, *Dt; const int4 *lvl, *grp, *st, *r1; };
-__device__ __forceinline__ GSm glu_smem() {
+__device__ __forceinline__ GSm glu_smem(int ns) {
   const DevNet& net = c_net;
   GSm g;
   g.y = smem_raw; g.xb = smem_raw + net.n; g.dinv = smem_raw + 2 * net.n;
@@ -505,9 +509,9 @@ __device__ __forceinline__ void tri_inv_upper(const double* src, int ld, int bs,
 // head (dense copies at X + sinv, ld 33) and the blocks of the dense tail (ld ldt).  After the
 // call the strictly-lower part of a block holds L^-1 (unit diagonal implicit) and the upper
 // part U^-1.  One warp per job, two jobs (L, U) per block, scratch = NW/2 tiles at X.
-__device__ __noinline__ void block_inverses(int subst) {
+__device__ __noinline__ void block_inverses(int subst, int ns) {
   const DevNet& net = c_net;
-  const GSm sm = glu_smem();
+  const GSm sm = glu_smem(ns);
   const int nt = net.nt, ldt = net.ldt, nbT = (nt + 31) >> 5, nbS = net.ss.nblkS;
   const int w = threadIdx.x >> 5, j = threadIdx.x & 31;
   double* zs = sm.X + (w >> 1) * (33 * 32);
@@ -564,8 +568,8 @@ __device__ __forceinline__ void glu_group(const uint32_t* __restrict__ ep, const
 
 // P = I - hl0*J and its LU, level-parallel ("gather") formulation: see HostNet::LevelLU.
 // The whole factor V (storage order) is in shared memory.  Returns 0 ok / 1 zero pivot.
-__device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned long long* ph, int subst) {
-  const GSm sm = glu_smem();
+__device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned long long* ph, int subst, int ns) {
+  const GSm sm = glu_smem(ns);
   const DevNet& net = c_net;
   const GluDev& g = net.glu;
   const int nh = net.nh, nt = net.nt, ldt = net.ldt;
@@ -772,13 +776,13 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
   // ---- dense tail
   const int dto = (int)(sm.Dt - smem_raw), pbo = (int)(sm.X - smem_raw);
   switch (nt >> 4) {
-    case 1: tail_lu<1>(dto, pbo, flag); break; case 2: tail_lu<2>(dto, pbo, flag); break;
-    case 3: tail_lu<3>(dto, pbo, flag); break; case 4: tail_lu<4>(dto, pbo, flag); break;
-    case 5: tail_lu<5>(dto, pbo, flag); break; case 6: tail_lu<6>(dto, pbo, flag); break;
-    case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
+    case 1: tail_lu<1>(dto, pbo, flag, ns); break; case 2: tail_lu<2>(dto, pbo, flag, ns); break;
+    case 3: tail_lu<3>(dto, pbo, flag, ns); break; case 4: tail_lu<4>(dto, pbo, flag, ns); break;
+    case 5: tail_lu<5>(dto, pbo, flag, ns); break; case 6: tail_lu<6>(dto, pbo, flag, ns); break;
+    case 7: tail_lu<7>(dto, pbo, flag, ns); break; default: tail_lu<8>(dto, pbo, flag, ns); break;
   }
   const long long t2b = clock64();
-  if ((subst & 11) != 11) block_inverses(subst);
+  if ((subst & 11) != 11) block_inverses(subst, ns);
   const int res = *flag;
   __syncthreads();
   if (tid == 0) {
@@ -792,7 +796,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
 // P = I - hl0*J (WK = J*CON, +1 on the diagonal; src/opkda1.f:1763-1764) and its numeric LU.
 // Returns (to all threads) 0 ok / 1 zero pivot.
 template <bool ALLSMEM>
-__device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, int* flag, unsigned long long* ph) {
+__device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, int* flag, unsigned long long* ph, int ns) {
   const DevNet& net = c_net;
   const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, tid = threadIdx.x;
@@ -905,13 +909,13 @@ __device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, in
   // ---- dense tail
   const int dto = (int)(sm.Dt - smem_raw), pbo = (int)(sm.X - smem_raw);
   switch (nt >> 4) {
-    case 1: tail_lu<1>(dto, pbo, flag); break; case 2: tail_lu<2>(dto, pbo, flag); break;
-    case 3: tail_lu<3>(dto, pbo, flag); break; case 4: tail_lu<4>(dto, pbo, flag); break;
-    case 5: tail_lu<5>(dto, pbo, flag); break; case 6: tail_lu<6>(dto, pbo, flag); break;
-    case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
+    case 1: tail_lu<1>(dto, pbo, flag, ns); break; case 2: tail_lu<2>(dto, pbo, flag, ns); break;
+    case 3: tail_lu<3>(dto, pbo, flag, ns); break; case 4: tail_lu<4>(dto, pbo, flag, ns); break;
+    case 5: tail_lu<5>(dto, pbo, flag, ns); break; case 6: tail_lu<6>(dto, pbo, flag, ns); break;
+    case 7: tail_lu<7>(dto, pbo, flag, ns); break; default: tail_lu<8>(dto, pbo, flag, ns); break;
   }
   long long t2b = clock64();
-  tail_block_inverses(sm);
+  tail_block_inverses(sm, ns);
   const int res = *flag;
   __syncthreads();
   if (tid == 0) {
@@ -1011,7 +1015,7 @@ __device__ __forceinline__ double block_subst(const double* T, int ld, int bs, b
 }
 
 __device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const uint32_t* ent, const uint16_t* rp,
-                                           const uint16_t* rows, double* tmp, bool upper, int subst) {
+                                           const uint16_t* rows, double* tmp, bool upper, int subst, int ns) {
   const DevNet& net = c_net;
   const int tid = threadIdx.x;
   const int kind = S.x & 255, lg = (S.x >> 8) & 255, lpr = 1 << lg, nrows = S.y & 0xffff, blk = S.y >> 16;
@@ -1099,9 +1103,9 @@ __device__ __forceinline__ void ell_apply(const EllDev& e, const EllRegs& R, con
   __syncthreads();
 }
 
-__device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst) {
+__device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst, int ns) {
   const DevNet& net = c_net;
-  const GSm sm = glu_smem();
+  const GSm sm = glu_smem(ns);
   const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
   const int tid = threadIdx.x;
   double* tmp = sm.X;            // [32] block right-hand side; the SpMV partials start behind it
@@ -1114,7 +1118,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst)
   ell_fetch(net.lcE, ws.lcE, R);           // lands while the head sweep runs
   for (int i = tid; i < n; i += NT) sm.xb[i] = sm.y[__ldg(net.perm + i)];
   __syncthreads();
-  for (int st = 0; st < net.ss.nf; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, false, subst);
+  for (int st = 0; st < net.ss.nf; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, false, subst, ns);
   const long long t1 = clock64();
   // ---- tail right-hand side: x_T -= L_C x_H
   ell_apply(net.lcE, R, sm.xb, sm.xb + nh, part);
@@ -1170,7 +1174,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst)
   // ---- head right-hand side: x_H -= U_B x_T
   ell_apply(net.ubE, R, sm.xb + nh, sm.xb, part);
   const long long t2 = clock64();
-  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, true, subst);
+  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, true, subst, ns);
   for (int i = tid; i < n; i += NT) sm.y[__ldg(net.perm + i)] = sm.xb[i];
   __syncthreads();
   if (tid == 0) {
@@ -1182,7 +1186,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst)
 
 // DSOLSS: sm.y <- P^{-1} sm.y (original species order in, original order out)
 // (wiped: P is pw*I, see DPRJS below)
-__device__ __forceinline__ void solve(Ws ws, Smem sm, bool wiped, double pw) {
+__device__ __forceinline__ void solve(Ws ws, Smem sm, bool wiped, double pw, int ns) {
   const DevNet& net = c_net;
   const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, tid = threadIdx.x;
@@ -1334,6 +1338,7 @@ struct Lsodes {      // COMMON /DLS001/ + /DLSS01/ (uniform across the CTA, held
 template <int EPT, bool GLU>
 __global__ void __launch_bounds__(NT, 1)
 integrate_kernel(const BatchArgs args) {
+  const int ns = args.net_slot;
   const DevNet& net = c_net;
   __shared__ int s_cell, s_flag;
   __shared__ unsigned long long s_ph[PH_COUNT];   // per-phase cycle counters (thread 0 only)
@@ -1443,18 +1448,18 @@ integrate_kernel(const BatchArgs args) {
     }
     if (tid == 0) { long long t = clock64(); ph[PH_RATES] += t - tc; }
     if (args.dbg_J) {   // diagnostics: in-kernel f and J at y0
-      eval_f(ks, x_off, DS, ph);
+      eval_f(ks, x_off, DS, ph, ns);
       for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = sm.savf[i];
       for (int q = tid; q < net.nstore; q += NT) ws.J[q] = 0.0;
       __syncthreads();
-      eval_jac(ks, x_off, ws.J, DS);
+      eval_jac(ks, x_off, ws.J, DS, ns);
       for (int q = tid; q < net.nstore; q += NT) args.dbg_J[(size_t)q * ncell + cell] = ws.J[q];
       __syncthreads();
       if (args.dbg_con != 0.0) {
-        const int fl = GLU ? factor_glu(ws, args.dbg_con, &s_flag, ph, net.glu.subst) : factor<false>(ws, sm, lay, args.dbg_con, &s_flag, ph);
+        const int fl = GLU ? factor_glu(ws, args.dbg_con, &s_flag, ph, net.glu.subst, ns) : factor<false>(ws, sm, lay, args.dbg_con, &s_flag, ph, ns);
         for (int i = tid; i < n; i += NT) sm.y[i] = sm.savf[i];
         __syncthreads();
-        if (GLU) solve_glu(ws, ph, net.glu.subst); else solve(ws, sm, false, 1.0);
+        if (GLU) solve_glu(ws, ph, net.glu.subst, ns); else solve(ws, sm, false, 1.0, ns);
         for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = fl ? nan("") : sm.y[i];
         __syncthreads();
       }
@@ -1464,9 +1469,17 @@ integrate_kernel(const BatchArgs args) {
     // ---- chem_evol_solve (src/chemistry.f90:391-588)
     const double t_max = args.tmax[cell], t_start = args.t0[cell];
     const double ratio = args.sp.ratio_tstep;
-    int n_record = (int)ceil(log((t_max - t_start) / args.dt_first[cell] * (ratio - 1.0) + 1.0) / log(ratio)) + 1;
+    // n_record of chem_evol_solve_prepare_run_once (src/chemistry.f90:1894-1899); nrec_max is only
+    // the capacity of touts/record: records beyond it are not stored, the loop is not shortened
+    const int n_record = (int)ceil(log((t_max - t_start) / args.dt_first[cell] * (ratio - 1.0) + 1.0) / log(ratio)) + 1;
     const int n_record_formula = n_record;
-    if (n_record > args.sp.nrec_max) n_record = args.sp.nrec_max;
+    // work budget: the reference's cpu_time clock (src/chemistry.f90:428-438, 480-494) replaced by
+    // the deterministic model  seconds = c_f NFE + c_jac NJE + c_lu NLU + c_solve n_solve + c_step NST
+    const bool budget = args.sp.max_runtime_allowed > 0.0;
+    const double max_runtime = args.sp.max_runtime_allowed;
+    const double max_time_per_step = 5.0 / (double)n_record * max_runtime;
+    double time_laststep = 0.0, runtime_laststep = 1.7976931348623157e308;
+    int premature = 0;
     double t = t_start, t_step = args.dt_first[cell], tout = t + t_step;
     int NERR = 0, nerr_c = 0, quality = 0, ISTATE = 1, n_record_real = 1;
     long long aNST = 0, aNFE = 0, aNJE = 0, aNLU = 0, nrestart = 0;
@@ -1483,6 +1496,7 @@ integrate_kernel(const BatchArgs args) {
     s.n_solve = s.n_cfail = s.n_efail = 0; s.wiped = 0; s.pw = 0.0;
     s.NQ = 1; s.L = 2; s.H = 0.0; s.TN = t; s.IHIT = false;
     auto record_out = [&](int irec) {   // touts(i) = t; record(:,i) = y
+      if (irec > args.sp.nrec_max) return;
       if (args.touts && tid == 0) args.touts[(size_t)(irec - 1) * ncell + cell] = t;
       if (args.record) {
         double* rp = args.record + (size_t)(irec - 1) * NEQ * ncell + cell;
@@ -1523,11 +1537,12 @@ integrate_kernel(const BatchArgs args) {
             case D_BLOCKC: {
               s.TN = t; s.NST = 0; s.H = 1.0;
               FORE { yh[e][0] = sm.y[i]; yh[e][2] = 0.0; yh[e][3] = 0.0; yh[e][4] = 0.0; yh[e][5] = 0.0; }
-              { long long ta = clock64(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
+              { long long ta = clock64(); eval_f(ks, x_off, DS, ph, ns); if (tid == 0) ph[PH_F] += clock64() - ta; }
               FORE yh[e][1] = sm.savf[i];
               s.NFE = 1;
               bool bad = false;
               FORE { const double ew = rt[e] * fabs(yh[e][0]) + at[e]; if (ew <= 0.0) bad = true; ewt[e] = 1.0 / ew; }
+              if (rtT * fabs(Tslot) + atT <= 0.0) bad = true;   // EWT(NEQ): the temperature slot
               if (__syncthreads_or(bad)) { ISTATE = -3; dl = D_RET; break; }
               s.TCRIT = t_max;
               if ((s.TCRIT - TOUT) * (TOUT - t) < 0.0) { ISTATE = -3; dl = D_RET; break; }
@@ -1583,6 +1598,7 @@ integrate_kernel(const BatchArgs args) {
               if ((s.NST - s.NSLAST) >= s.MXSTEP) { ISTATE = -1; dl = D580; break; }
               bool bad = false;
               FORE { const double ew = rt[e] * fabs(yh[e][0]) + at[e]; if (ew <= 0.0) bad = true; ewt[e] = 1.0 / ew; }
+              if (rtT * fabs(Tslot) + atT <= 0.0) bad = true;
               if (__syncthreads_or(bad)) { ISTATE = -6; dl = D580; break; }
               dl = D270;
               break;
@@ -1668,7 +1684,7 @@ integrate_kernel(const BatchArgs args) {
                     M = 0;
                     FORE sm.y[i] = yh[e][0];
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); eval_f(ks, x_off, DS, ph, ns); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     if (s.IPUP <= 0) { pc = L250; break; }
@@ -1701,7 +1717,7 @@ integrate_kernel(const BatchArgs args) {
                         s.JCUR = 1; s.NJE = s.NJE + 1; s.NSLJ = s.NST; s.IPLOST = 0; s.CONMIN = fabs(CON);
                         if (tid == 0) ph[PH_VEC] += clock64() - tv;
                         long long ta = clock64();
-                        eval_jac(ks, x_off, ws.J, DS);
+                        eval_jac(ks, x_off, ws.J, DS, ns);
                         if (tid == 0) ph[PH_JAC] += clock64() - ta;
                         tv = clock64();
                         s.wiped = 0;
@@ -1712,7 +1728,7 @@ integrate_kernel(const BatchArgs args) {
                         flag = (s.pw == 0.0 || isnan(s.pw)) ? 1 : 0;
                       } else {
                         if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                        flag = GLU ? factor_glu(ws, CON, &s_flag, ph, subst) : factor<false>(ws, sm, lay, CON, &s_flag, ph);
+                        flag = GLU ? factor_glu(ws, CON, &s_flag, ph, subst, ns) : factor<false>(ws, sm, lay, CON, &s_flag, ph, ns);
                         tv = clock64();
                       }
                       s.CON0 = CON;
@@ -1731,8 +1747,8 @@ integrate_kernel(const BatchArgs args) {
                     __syncthreads();
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
                     { long long ta = clock64(); if (s.wiped) { for (int i = tid; i < n; i += NT) sm.y[i] = sm.y[i] / s.pw; __syncthreads(); }
-                      else if (GLU) solve_glu(ws, ph, subst);
-                      else solve(ws, sm, false, s.pw);
+                      else if (GLU) solve_glu(ws, ph, subst, ns);
+                      else solve(ws, sm, false, s.pw, ns);
                       if (tid == 0) ph[PH_SOLVE] += clock64() - ta; }
                     tv = clock64();
                     s.n_solve++;
@@ -1746,7 +1762,7 @@ integrate_kernel(const BatchArgs args) {
                     if (M >= 2 && DEL > 2.0 * DELP) { pc = L410; break; }
                     DELP = DEL;
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); __syncthreads(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); __syncthreads(); eval_f(ks, x_off, DS, ph, ns); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     pc = L270;
@@ -1863,7 +1879,7 @@ integrate_kernel(const BatchArgs args) {
                     __syncthreads();
                     FORE sm.y[i] = yh[e][0];
                     if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); __syncthreads(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += clock64() - ta; }
+                    { long long ta = clock64(); __syncthreads(); eval_f(ks, x_off, DS, ph, ns); if (tid == 0) ph[PH_F] += clock64() - ta; }
                     tv = clock64();
                     s.NFE = s.NFE + 1;
                     FORE yh[e][1] = s.H * sm.savf[i];
@@ -1970,8 +1986,18 @@ integrate_kernel(const BatchArgs args) {
       __syncthreads();
       record_out(irec);
       n_record_real = irec;
-      if (GLU && !second_try && s.n_cfail > 4000) { redo_mask = subst ^ 2; break; }
-      if (aNST + s.NST > 250000) break;   // runaway guard: 2.4x the heaviest cell that completes normally
+      if (GLU && !second_try && !(net.glu.subst & 16) && s.n_cfail > 4000) { redo_mask = subst ^ 2; break; }
+      if (budget) {
+        const double time_thisstep = net.rt_coef[0] * (double)(aNFE + s.NFE) + net.rt_coef[1] * (double)(aNJE + s.NJE) +
+                                     net.rt_coef[2] * (double)(aNLU + s.NLU) + net.rt_coef[3] * (double)s.n_solve +
+                                     net.rt_coef[4] * (double)(aNST + s.NST);
+        const double runtime_thisstep = time_thisstep - time_laststep;
+        if (runtime_thisstep > fmax(10.0 * runtime_laststep, 0.5 * max_runtime) || time_thisstep > max_runtime) {
+          premature = 1; break;   // 'Premature finish', src/chemistry.f90:482-488
+        }
+        if (runtime_thisstep > max_time_per_step) ISTATE = 1;
+        time_laststep = time_thisstep; runtime_laststep = runtime_thisstep;
+      }
       if (t >= t_max) break;
       if (ISTATE < 0) {
         NERR += 1; nerr_c += 1;
@@ -1998,7 +2024,7 @@ integrate_kernel(const BatchArgs args) {
     }
     // an abnormal end of the first attempt (unphysical abundances, illegal input, DLSODES -7)
     // earns the same second chance as the corrector-failure count
-    if (GLU && !second_try && redo_mask < 0 && (quality & (256 | 512 | 1024))) redo_mask = subst ^ 2;
+    if (GLU && !second_try && !(net.glu.subst & 16) && redo_mask < 0 && (quality & (256 | 512 | 1024))) redo_mask = subst ^ 2;
     if (redo_mask >= 0) {
       cNST = aNST + s.NST; cNFE = aNFE + s.NFE; cNJE = aNJE + s.NJE; cNLU = aNLU + s.NLU;
       cSOL = s.n_solve; cCF = s.n_cfail; cEF = s.n_efail;
@@ -2009,7 +2035,7 @@ integrate_kernel(const BatchArgs args) {
     s.n_solve += (int)cSOL; s.n_cfail += (int)cCF; s.n_efail += (int)cEF;
     cNST = cNFE = cNJE = cNLU = cSOL = cCF = cEF = 0;
     // records after an early exit are filled with the last state (src/chemistry.f90:570-575)
-    for (int r2 = n_record_real + 1; r2 <= args.sp.nrec_max; ++r2) record_out(r2);
+    if (args.touts || args.record) for (int r2 = n_record_real + 1; r2 <= args.sp.nrec_max; ++r2) record_out(r2);
     if (NERR > (int)(0.1f * (float)n_record_formula)) quality += 1;
     if (t <= 0.5 * t_max) quality += 2;
     // ---- write results
@@ -2021,7 +2047,10 @@ integrate_kernel(const BatchArgs args) {
       double* st = args.stats + cell;
       const double sv[RACG_NSTAT] = {(double)aNST, (double)aNFE, (double)aNJE, (double)aNLU, (double)s.NQU,
                                      (double)s.n_solve, (double)NERR, (double)nrestart, (double)s.n_cfail,
-                                     (double)s.n_efail, (double)n_record_real, (double)ISTATE, s.HU, 0, 0, 0};
+                                     (double)s.n_efail, (double)n_record_real, (double)ISTATE, s.HU,
+                                     net.rt_coef[0] * (double)aNFE + net.rt_coef[1] * (double)aNJE + net.rt_coef[2] * (double)aNLU +
+                                         net.rt_coef[3] * (double)s.n_solve + net.rt_coef[4] * (double)aNST,
+                                     (double)premature, 0};
       for (int k = 0; k < RACG_NSTAT; ++k) st[(size_t)k * ncell] = sv[k];
       ph[PH_NCELL] += 1;
     }
@@ -2041,15 +2070,55 @@ integrate_kernel(const BatchArgs args) {
 //   [tab, +blob)         tables of the staged head solves
 // cost of every cell of the batch just integrated (in units of one triangular solve), kept by
 // the handle: when the next batch has the same number of cells -- the disk code re-integrates
-// the same grid every structure iteration -- its work queue is served heaviest first
-__global__ void cost_kernel(int ncell, const double* __restrict__ stats, float* __restrict__ cost) {
+// the same grid every structure iteration -- its work queue is served heaviest first.  The
+// order is built on the device by a counting sort over 4096 logarithmic cost buckets (no host
+// synchronisation; the order inside a bucket is arbitrary, results do not depend on it).
+__device__ __forceinline__ int cost_bucket(float c) {
+  int q = (int)(log2f(c + 1.0f) * 128.0f);
+  q = q < 0 ? 0 : (q > 4095 ? 4095 : q);
+  return 4095 - q;     // heaviest first
+}
+__global__ void cost_kernel(int ncell, const double* __restrict__ stats, float* __restrict__ cost, int* __restrict__ hist) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < ncell) cost[c] = (float)(10.0 * stats[(size_t)3 * ncell + c] + stats[(size_t)5 * ncell + c] +
-                                   0.5 * stats[(size_t)1 * ncell + c]);
+  if (c < ncell) {
+    const float v = (float)(10.0 * stats[(size_t)3 * ncell + c] + stats[(size_t)5 * ncell + c] +
+                            0.5 * stats[(size_t)1 * ncell + c]);
+    cost[c] = v;
+    atomicAdd(&hist[cost_bucket(v)], 1);
+  }
 }
-void launch_cost(int ncell, const double* stats, float* cost, cudaStream_t st) {
-  cost_kernel<<<(ncell + 255) / 256, 256, 0, st>>>(ncell, stats, cost);
+__global__ void __launch_bounds__(1024) cost_scan_kernel(int* __restrict__ hist) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  int v[4], s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { v[k] = hist[4 * t + k]; s += v[k]; }
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int add = (t >= o) ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += add;
+    __syncthreads();
+  }
+  int base = part[t] - s;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { hist[4 * t + k] = base; base += v[k]; }
 }
+__global__ void cost_scatter_kernel(int ncell, const float* __restrict__ cost, int* __restrict__ hist, int* __restrict__ order) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncell) order[atomicAdd(&hist[cost_bucket(cost[c])], 1)] = c;
+}
+cudaError_t launch_cost_order(int ncell, const double* stats, float* cost, int* order, int* hist, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(hist, 0, 4096 * sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  cost_kernel<<<(ncell + 255) / 256, 256, 0, st>>>(ncell, stats, cost, hist);
+  cost_scan_kernel<<<1, 1024, 0, st>>>(hist);
+  cost_scatter_kernel<<<(ncell + 255) / 256, 256, 0, st>>>(ncell, cost, hist, order);
+  return cudaGetLastError();
+}
+
+int integrate_threads() { return NT; }
 
 size_t integrate_smem_bytes(DevNet& net) {
   if (net.glu.on) {
@@ -2084,11 +2153,17 @@ size_t integrate_ws_doubles(const DevNet& net) {
   return (w + 15) & ~(size_t)15;
 }
 
+#undef c_net
+// one-time upload of a handle's descriptor into its constant-memory slot (racg_network_create)
+cudaError_t upload_net_slot(int slot, const DevNet& net) {
+  if (slot < 0 || slot >= RACG_MAX_NETS) return cudaErrorInvalidValue;
+  return cudaMemcpyToSymbol(c_nets, &net, sizeof(DevNet), (size_t)slot * sizeof(DevNet), cudaMemcpyHostToDevice);
+}
+
 cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nblocks, size_t smem,
                              cudaStream_t stream) {
   if (net.nt > 16 * MAXTL || (net.nt & 15)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_net, &net, sizeof(DevNet), 0, cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess) return e;
+  cudaError_t e;
   const Layout L = make_layout(net);
   const bool all = L.glu != 0;
   auto go = [&](auto kern) -> cudaError_t {
