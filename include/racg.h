@@ -115,8 +115,7 @@ int racg_use_devices(racg_handle* h, int ndev, const int* devices);
 int racg_device_count(const racg_handle* h);
 /* options: "warm_order" (default 1: a batch with as many cells as the previous one is queued
  * heaviest-first from that batch's per-cell cost; order only, results do not depend on it),
- * "level_lu" (default 1; 0 forces the generic factorisation path, diagnostics),
- * "block_mode" (diagnostics: how diagonal blocks of the triangular solves are treated) */
+ * "level_lu" (default 1; 0 forces the generic factorisation path, diagnostics) */
 int racg_set_option(racg_handle* h, const char* name, double value);
 /* human-readable summary of the shared symbolic factorisation and schedules */
 int racg_network_describe(const racg_handle* h, char* buf, int len);

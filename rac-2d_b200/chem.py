@@ -42,7 +42,9 @@ class SolveParams(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libracg.so")
+    # RACG_LIB: A/B measurements of build variants (e.g. libracg_nt256.so) from the Python
+    # harness; the C library itself reads no environment variables
+    return os.environ.get("RACG_LIB") or os.path.join(_HERE, "libracg.so")
 
 
 def build(force=False):

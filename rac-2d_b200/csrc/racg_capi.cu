@@ -23,8 +23,8 @@ namespace racg {
 int integrate_threads();
 size_t integrate_smem_bytes(DevNet& net);
 size_t integrate_ws_doubles(const DevNet& net);
-cudaError_t upload_net_slot(int slot, const DevNet& net);
-cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nblocks, size_t smem, cudaStream_t stream);
+cudaError_t launch_integrate(const DevNet& net, unsigned long long net_id, int device, const BatchArgs& args, int nblocks,
+                             size_t smem, cudaStream_t stream);
 cudaError_t launch_cost_order(int ncell, const double* stats, float* cost, int* order, int* hist, cudaStream_t st);
 cudaError_t launch_cost(int ncell, const double* stats, float* cost, cudaStream_t st);
 // racg_batch.cu
@@ -41,12 +41,14 @@ static thread_local std::string g_err;
 static int fail(int code, const std::string& s) { g_err = s; return code; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(RACG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
-// constant-memory slots of the integrator, per device of this process
-static std::mutex g_slot_mu;
-static unsigned char g_slot_used[64][RACG_MAX_NETS];
+// identity of a device context's descriptor (never reused): tells launch_integrate whether the
+// device's constant memory already holds it
+static std::mutex g_id_mu;
+static unsigned long long g_next_id = 1;
 
 struct DevCtx {
-  int device = -1, nsm = 0, slot = -1;
+  int device = -1, nsm = 0;
+  unsigned long long net_id = 0;   // changes whenever dn changes
   DevNet dn;
   JacColTables jc;
   std::vector<void*> allocs;
@@ -69,7 +71,7 @@ struct racg_handle {
   std::vector<DevCtx*> dev;        // dev[0]: the device current at racg_network_create
   long launches = 0;
   // options (racg_set_option)
-  int warm_order = 1, level_lu = 1, block_mode = 0;
+  int warm_order = 1, level_lu = 1;
   // warm scheduling (host side): cost of every cell of the previous host-pointer batch
   std::vector<float> last_cost;
   double* dbg_J = nullptr;   // set only inside racg_debug_fjac
@@ -156,7 +158,6 @@ static void destroy_ctx(DevCtx* c) {
     if (c->d_arena) cudaFree(c->d_arena);
     if (c->h_arena) cudaFreeHost(c->h_arena);
     if (c->stream) cudaStreamDestroy(c->stream);
-    if (c->slot >= 0 && c->device < 64) { std::lock_guard<std::mutex> lk(g_slot_mu); g_slot_used[c->device][c->slot] = 0; }
   }
   delete c;
 }
@@ -166,14 +167,13 @@ static int finish_ctx(racg_handle* h, DevCtx* c) {
   const HostNet& hn = h->hn;
   DevNet& dn = c->dn;
   dn.glu.on = (hn.glu.nlev > 0 && hn.ss.nent > 0 && h->level_lu) ? 1 : 0;
-  dn.glu.subst = h->block_mode;
   c->smem_int = integrate_smem_bytes(dn);   // also plans the scratch region of the level-parallel mode
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, c->device));
   if (c->smem_int > (size_t)prop.sharedMemPerBlockOptin)
     return fail(RACG_ERR_UNSUPPORTED, "network too large for the shared-memory layout of the integrator: " +
                                       std::to_string(c->smem_int) + " B needed");
-  CK(upload_net_slot(c->slot, dn));
+  { std::lock_guard<std::mutex> lk(g_id_mu); c->net_id = g_next_id++; }
   return 0;
 }
 
@@ -187,11 +187,6 @@ static int create_ctx(racg_handle* h, int device, DevCtx** out) {
   CK(cudaGetDeviceProperties(&prop, device));
   c->nsm = prop.multiProcessorCount;
   if (device >= 64) return fail(RACG_ERR_ARG, "device index above 63");
-  {
-    std::lock_guard<std::mutex> lk(g_slot_mu);
-    for (int s = 0; s < RACG_MAX_NETS && c->slot < 0; ++s) if (!g_slot_used[device][s]) { g_slot_used[device][s] = 1; c->slot = s; }
-  }
-  if (c->slot < 0) return fail(RACG_ERR_UNSUPPORTED, "more than " + std::to_string(RACG_MAX_NETS) + " live handles on one device");
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   const HostNet& hn = h->hn;
   DevNet& dn = c->dn;
@@ -330,7 +325,6 @@ static inline float cell_cost(const double* stats, size_t ncell, size_t c) {
 static int solve_on_ctx(racg_handle* h, DevCtx* c, const BatchArgs& a0, bool device_order, cudaStream_t st) {
   BatchArgs a = a0;
   const int ncell = a.ncell;
-  a.net_slot = c->slot;
   a.queue = c->d_queue; a.ws = c->d_ws; a.ws_stride = c->ws_stride; a.phase = c->d_phase;
   a.dbg_J = h->dbg_J; a.dbg_con = h->dbg_con;
   if (device_order) {
@@ -348,7 +342,7 @@ static int solve_on_ctx(racg_handle* h, DevCtx* c, const BatchArgs& a0, bool dev
   CK(cudaMemsetAsync(c->d_queue, 0, sizeof(int), st));
   CK(cudaMemsetAsync(c->d_phase, 0, RACG_NPHASE * sizeof(unsigned long long), st));
   const int nblocks = ncell < c->nblocks ? ncell : c->nblocks;
-  CK(launch_integrate(c->dn, a, nblocks, c->smem_int, st));
+  CK(launch_integrate(c->dn, c->net_id, c->device, a, nblocks, c->smem_int, st));
   h->launches += 1;
   if (device_order && !h->dbg_J) {
     CK(launch_cost_order(ncell, a.stats, c->d_cost, c->d_order, c->d_hist, st));
@@ -467,7 +461,6 @@ int racg_set_option(racg_handle* h, const char* name, double value) {
   const std::string k = name;
   if (k == "warm_order") h->warm_order = value != 0.0;
   else if (k == "level_lu") h->level_lu = value != 0.0;
-  else if (k == "block_mode") h->block_mode = (int)value;
   else return fail(RACG_ERR_ARG, "unknown option: " + k);
   if (k != "warm_order" && !h->dev.empty()) {
     DeviceGuard guard;

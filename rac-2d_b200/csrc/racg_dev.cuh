@@ -4,8 +4,6 @@
 #include <vector_types.h>
 #include "../../include/racg.h"
 
-#define RACG_MAX_NETS 8   // constant-memory slots = live handles per device (racg_integrate.cu)
-
 namespace racg {
 
 struct GatherDev {
@@ -38,7 +36,6 @@ struct EllDev {
 // constant-cache miss.
 struct GluDev {
   int on, nlev, zpos, voff;
-  int subst;                  // bits: 1 L blocks, 2 U blocks of the tail, 8 U blocks of the S rows by substitution
   int ngrp, ndesc, doff;      // descriptor block: [lvl (nlev+1) | grp (ngrp) | stages (nst) | rank-1 pairs]; doff = offset in smem (doubles)
   const uint32_t* piv; const uint32_t* mul; const uint32_t* ent; const uint16_t* tgt;
   const uint16_t* r1tgt;      // rank-1 levels: 4 target positions per (row chunk, column chunk, lane)
@@ -97,7 +94,6 @@ struct DevNet {
 
 struct BatchArgs {
   int ncell;
-  int net_slot;              // constant-memory slot of the handle's DevNet
   const double* cellpar;     // [NPAR][ncell]
   const double* y0;          // [NEQ][ncell]
   const double* rtol;        // [NEQ][ncell] or null

@@ -26,14 +26,33 @@
 // register-tiled dense tail, explicit block inverses); solves: solve_glu (staged sweeps).
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <mutex>
 #include "racg_dev.cuh"
 #include "racg_rates.cuh"
 
 namespace racg {
 
-constexpr int NT = 256;           // threads per CTA (16 x 16 grid for the dense tail LU)
+#ifndef RACG_NT
+#define RACG_NT 256
+#endif
+constexpr int NT = RACG_NT;       // threads per CTA = per cell (256 or 512)
 constexpr int NW = NT / 32;       // warps per CTA
-constexpr int MAXTL = 8;          // tail tile edge per thread: nt <= 16 * MAXTL = 128
+constexpr int TJ = NT / 16;       // dense tail LU: 16 x TJ thread grid
+constexpr int LPB = NT / 32;      // lanes per row in the 32-row block stages of the solves
+constexpr int LGLPB = (LPB == 8) ? 3 : 4;
+constexpr int MAXTL = 8;          // tail rows per thread: nt <= 16 * MAXTL = 128
+static_assert(NT == 256 || NT == 512, "RACG_NT must be 256 or 512");
+
+// per-phase cycle counters (racg_phase_cycles): compiled in only for the profiling build
+// (make PROF=1 ../libracg_prof.so); the production build keeps only the total and the cell count
+#ifndef RACG_PHASE_TIMERS
+#define RACG_PHASE_TIMERS 0
+#endif
+#if RACG_PHASE_TIMERS
+__device__ __forceinline__ long long pclock() { return clock64(); }
+#else
+__device__ __forceinline__ long long pclock() { return 0; }
+#endif
 
 enum Phase { PH_RATES = 0, PH_F, PH_JAC, PH_FACT_HEAD, PH_FACT_SCHUR, PH_FACT_TAIL, PH_SOLVE,
              PH_VEC, PH_G_LOOP, PH_TOTAL, PH_NCELL, PH_PBUILD, PH_TAILINV, PH_S_FWD, PH_S_TAIL, PH_S_BWD,
@@ -43,7 +62,7 @@ struct Smem {
   double* y;      // [n]  argument of f / right-hand side and result of the linear solve
   double* savf;   // [n]  f(y)
   double* xb;     // solve vector in elimination order: aliases savf (dead while P x = b is solved)
-  double* dinv;   // [nh] 1 / pivot of the head rows
+  double* dinv;   // [n] 1 / pivot: head rows, then the dense tail
   double* par;    // [32]
   double* red;    // [2*NW]
   double* Dt;     // [ldt*nt] dense tail, column-major; diagonal 32-blocks hold their inverses
@@ -73,13 +92,15 @@ struct Layout { int hh_smem, ub_smem, nwr, glu; size_t xdoubles, total, voff; };
 // that the compiler emits shared-space (LDS/STS) instead of generic accesses
 extern __shared__ __align__(16) double smem_raw[];
 
-// Network descriptors in constant memory: every device function reads its network through the
-// constant cache (passing the ~1 KB struct by reference would spill it to local memory).  One
-// slot per live handle of the device, written once by racg_network_create (upload_net_slot) and
-// never touched by a launch: handles with different networks, or on different streams, do not
-// share any constant state.  Device functions take the slot index `ns`.
-__constant__ DevNet c_nets[RACG_MAX_NETS];
-#define c_net (c_nets[ns])
+// Network descriptor in constant memory: every device function reads it as a direct constant-
+// bank operand (passing the ~1 KB struct by reference would spill it to local memory, and an
+// indexed array of descriptors costs a separate LDC per use: +17 % run time was measured).
+// There is ONE descriptor per device, so launch_integrate() serialises the integrator launches
+// of all handles of a device through an event: a launch first waits for the previous
+// integrator launch on that device (whatever handle or stream issued it), then uploads its own
+// descriptor in stream order -- skipped when the device already holds it.  The persistent
+// kernel fills every SM, so two integrator launches could not overlap anyway.
+__constant__ DevNet c_net;
 
 // Shared-memory plan.  Preferred: everything (head x head block, the factorisation's copy
 // of U_B) on chip AND the total under 196 KB, so that the SM keeps >= 60 KB of L1 for the
@@ -92,7 +113,7 @@ __host__ __device__ inline Layout make_layout(const DevNet& net) {
   const size_t nthin_f = (size_t)(net.nh - net.flev_nfat_rows), nthin_b = (size_t)(net.nh - net.su_nfat_rows);
   const size_t tables = ((size_t)net.n_hh * 2 + (nthin_f + nthin_b) * 16 +
                          (size_t)(net.nflev + net.nsu + 2) * 4 + 64 + 7) / 8;
-  const size_t fixed = 2 * n + net.nh + 32 + 2 * NW + (size_t)net.ldt * net.nt + tables;
+  const size_t fixed = 2 * n + n + 32 + 2 * NW + (size_t)net.ldt * net.nt + tables;   // y, savf, 1/pivots (head + tail)
   // scratch X: fluxes + gather partials | dflux + partials | SpMV partials | tolerance staging |
   // tail_lu publication buffers; during the factorisation: nwr work rows + U_B values + U_B columns
   size_t x_f = R + (size_t)net.rhs.npartial + 32;
@@ -117,7 +138,7 @@ __host__ __device__ inline Layout make_layout(const DevNet& net) {
     if (x < x_f) x = x_f;
     if (fixed + net.n_hh + x <= big) { L.nwr = nwr; ok = true; }
   }
-  if (!ok) { L.nwr = NW; L.hh_smem = 0; L.ub_smem = 0; }   // large networks: L2 workspace
+  if (!ok) { L.nwr = NW > 8 ? 8 : NW; L.hh_smem = 0; L.ub_smem = 0; }   // large networks: L2 workspace
   size_t x = (size_t)L.nwr * n + (L.ub_smem ? ubx : 0);
   if (x < x_f) x = x_f;
   L.xdoubles = x;
@@ -205,7 +226,7 @@ __device__ __forceinline__ void run_gather(const GatherDev& g, const double* src
 
 // flux of reaction r (branches of chem_ode_f, src/disk.f90:4583-4643)
 __device__ __forceinline__ double flux_of(uint32_t w, double k, const double* y,
-                                          double DS, int ns) {
+                                          double DS) {
   const int kind = (w >> 20) & 3;
   const double y1 = y[w & 1023];
   if (kind == FK_ONE) return k * y1;
@@ -227,7 +248,7 @@ __device__ __forceinline__ double flux_of(uint32_t w, double k, const double* y,
 // d flux / d y(r1) (which = 0) or d flux / d y(r2) (which = 1)
 // (branches of chem_ode_jac, src/disk.f90:4765-4866)
 __device__ __forceinline__ double dflux_of(uint32_t w, double k, const double* y,
-                                           double DS, int which, int ns) {
+                                           double DS, int which) {
   const int kind = (w >> 20) & 3;
   const int r1 = w & 1023, r2 = (w >> 10) & 1023;
   if (kind == FK_ONE) return which == 0 ? k : 0.0;
@@ -253,7 +274,7 @@ __device__ __forceinline__ double dflux_of(uint32_t w, double k, const double* y
 // chem_ode_f: savf = S * flux(k, y).  k streamed from the workspace (L2), fluxes in the
 // scratch region X (x_off = its offset in the shared-memory block); y = smem_raw[0..n),
 // savf = smem_raw[n..2n)
-__device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off, double DS, unsigned long long* ph, int ns) {
+__device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off, double DS, unsigned long long* ph) {
   const DevNet& net = c_net;
   const int R = net.R;
   double* const fx = smem_raw + x_off;
@@ -261,7 +282,7 @@ __device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off,
   const double* const yv = smem_raw;
   double* const out = smem_raw + net.n;
   __syncthreads();   // y was just written by its owner threads
-  const long long tf0 = clock64();
+  const long long tf0 = pclock();
   for (int r0 = threadIdx.x; r0 < R; r0 += 4 * NT) {
     double kk[4]; uint32_t ww[4];
 #pragma unroll
@@ -273,25 +294,25 @@ __device__ __forceinline__ void eval_f(const double* __restrict__ ks, int x_off,
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int r = r0 + u * NT;
-      if (r < R) fx[r] = flux_of(ww[u], kk[u], yv, DS, ns);
+      if (r < R) fx[r] = flux_of(ww[u], kk[u], yv, DS);
     }
   }
   for (int i = threadIdx.x; i < net.n; i += NT) out[i] = 0.0;
   __syncthreads();
-  const long long tg = clock64();
+  const long long tg = pclock();
   run_gather<false>(net.rhs, fx, out, px);
-  if (threadIdx.x == 0) { ph[PH_F_FLUX] += tg - tf0; ph[PH_F_GATHER] += clock64() - tg; }
+  if (threadIdx.x == 0) { ph[PH_F_FLUX] += tg - tf0; ph[PH_F_GATHER] += pclock() - tg; }
 }
 
 // chem_ode_jac for all columns at once -> ws.J (two passes over the reactions)
-__device__ __forceinline__ void eval_jac(const double* __restrict__ ks, int x_off, double* J, double DS, int ns) {
+__device__ __forceinline__ void eval_jac(const double* __restrict__ ks, int x_off, double* J, double DS) {
   const DevNet& net = c_net;
   double* const dfx = smem_raw + x_off;
   double* const px = dfx + net.R;
   const double* const yv = smem_raw;
   __syncthreads();
   for (int pass = 0; pass < 2; ++pass) {
-    for (int r = threadIdx.x; r < net.R; r += NT) dfx[r] = dflux_of(__ldg(net.fw + r), __ldcg(ks + r), yv, DS, pass, ns);
+    for (int r = threadIdx.x; r < net.R; r += NT) dfx[r] = dflux_of(__ldg(net.fw + r), __ldcg(ks + r), yv, DS, pass);
     __syncthreads();
     run_gather<true>(net.jac[pass], dfx, J, px);
   }
@@ -299,135 +320,85 @@ __device__ __forceinline__ void eval_jac(const double* __restrict__ ks, int x_of
 
 // ---------------------------------------------------------------------------
 // dense no-pivot LU of the nt x nt tail block held in sm.Dt (column-major, ld = ldt),
-// register tiled: thread (ti,tj) of a 16x16 grid owns rows ti+16a, cols tj+16b.
+// register tiled: thread (ti,tj) of a 16 x TJ grid owns rows ti+16a (a < TL) and columns
+// tj+TJ*b (b < TC = ceil(16 TL / TJ); columns >= nt are padding and never touch memory).
 // One barrier per elimination step: the owners of column k / row k publish the unscaled
 // column, the row and the pivot; everybody scales and updates its tile.
 // helpers with a compile-time tile index so that register arrays stay in registers
 template <int TL, int B> struct PubCol { template <class T> static __device__ __forceinline__ void go(const T& t, double* pc, int ti) {
 #pragma unroll
   for (int a = 0; a < TL; ++a) pc[ti + 16 * a] = t[a][B]; } };
-template <int TL, int A> struct PubRow { template <class T> static __device__ __forceinline__ void go(const T& t, double* pr, int tj) {
+template <int TC, int A> struct PubRow { template <class T> static __device__ __forceinline__ void go(const T& t, double* pr, int tj) {
 #pragma unroll
-  for (int b = 0; b < TL; ++b) pr[tj + 16 * b] = t[A][b]; } };
+  for (int b = 0; b < TC; ++b) pr[tj + TJ * b] = t[A][b]; } };
 
-// one elimination step for the tile block row/col KA (uniform across the CTA)
-template <int TL, int KA>
-__device__ __forceinline__ void tail_step(double (&t)[TL][TL], int k, int kr, int ti, int tj, double* pc, double* pr, int* flag) {
-  if (tj == kr) PubCol<TL, KA>::go(t, pc, ti);
-  if (ti == kr) PubRow<TL, KA>::go(t, pr, tj);
+// one elimination step k = 16*KA + kr (KA uniform across the CTA): tile row index KA, tile
+// column index KC = k / TJ
+template <int TL, int TC, int KA>
+__device__ __forceinline__ void tail_step(double (&t)[TL][TC], int k, int ti, int tj, double* pc, double* pr, int* flag, double* rdt) {
+  constexpr int KC = (16 * KA) / TJ;
+  const int kr = k & 15, kc = k & (TJ - 1);
+  if (tj == kc) PubCol<TL, KC>::go(t, pc, ti);
+  if (ti == kr) PubRow<TC, KA>::go(t, pr, tj);
   __syncthreads();
   const double piv = pc[k];
   if (piv == 0.0 || isnan(piv)) { if (threadIdx.x == 0) *flag = 1; }
   const double inv = 1.0 / piv;
-  // rows a > KA and columns b > KA are fully active, a == KA / b == KA are active for ti > kr / tj > kr
-  double lr[TL], uc[TL];
+  if (threadIdx.x == 0) rdt[k] = inv;     // 1 / U(k,k) for the back substitution
+  // rows a > KA and columns b > KC are fully active, a == KA / b == KC are active for ti > kr / tj > kc
+  double lr[TL], uc[TC];
 #pragma unroll
   for (int a = KA; a < TL; ++a) lr[a] = pc[ti + 16 * a] * inv;
 #pragma unroll
-  for (int b = KA; b < TL; ++b) uc[b] = pr[tj + 16 * b];
-  const bool rowKA = ti > kr, colKA = tj > kr;
+  for (int b = KC; b < TC; ++b) uc[b] = pr[tj + TJ * b];
+  const bool rowKA = ti > kr, colKC = tj > kc;
   if (!rowKA) lr[KA] = 0.0;
-  if (!colKA) uc[KA] = 0.0;
+  if (!colKC) uc[KC] = 0.0;
 #pragma unroll
   for (int a = KA; a < TL; ++a)
 #pragma unroll
-    for (int b = KA; b < TL; ++b) t[a][b] -= lr[a] * uc[b];
+    for (int b = KC; b < TC; ++b) t[a][b] -= lr[a] * uc[b];
   // column k keeps the multipliers (its uc was zero, so t was untouched above)
-  if (tj == kr) {
+  if (tj == kc) {
 #pragma unroll
-    for (int a = KA + 1; a < TL; ++a) t[a][KA] = lr[a];
-    if (rowKA) t[KA][KA] = lr[KA];
+    for (int a = KA + 1; a < TL; ++a) t[a][KC] = lr[a];
+    if (rowKA) t[KA][KC] = lr[KA];
   }
 }
 
 template <int TL>
-__device__ __noinline__ void tail_lu(int dt_off, int pub_off, int* flag, int ns) {
+__device__ __noinline__ void tail_lu(int dt_off, int pub_off, int* flag) {   // reciprocal pivots -> dinv[nh + k]
   const DevNet& net = c_net;
+  constexpr int TC = (16 * TL + TJ - 1) / TJ;
   const int nt = net.nt, ldt = net.ldt;
   double* const Dt = smem_raw + dt_off;     // offsets into the shared-memory block: keeps
   double* const pub = smem_raw + pub_off;   // the accesses in the shared address space
-  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
-  double t[TL][TL];
+  double* const rdt = smem_raw + 2 * net.n + net.nh;
+  const int ti = threadIdx.x / TJ, tj = threadIdx.x & (TJ - 1);
+  double t[TL][TC];
 #pragma unroll
   for (int a = 0; a < TL; ++a)
 #pragma unroll
-    for (int b = 0; b < TL; ++b) t[a][b] = Dt[(tj + 16 * b) * ldt + ti + 16 * a];
+    for (int b = 0; b < TC; ++b) t[a][b] = (tj + TJ * b < nt) ? Dt[(tj + TJ * b) * ldt + ti + 16 * a] : 0.0;
   for (int k = 0; k < nt; ++k) {
     double* pc = pub + (k & 1) * (2 * 128 + 8);
     double* pr = pc + 128;
-    const int ka = k >> 4, kr = k & 15;
-    switch (ka) {   // uniform across the CTA
-      case 0: tail_step<TL, 0>(t, k, kr, ti, tj, pc, pr, flag); break;
-      case 1: if (TL > 1) tail_step<TL, (TL > 1 ? 1 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
-      case 2: if (TL > 2) tail_step<TL, (TL > 2 ? 2 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
-      case 3: if (TL > 3) tail_step<TL, (TL > 3 ? 3 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
-      case 4: if (TL > 4) tail_step<TL, (TL > 4 ? 4 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
-      case 5: if (TL > 5) tail_step<TL, (TL > 5 ? 5 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
-      case 6: if (TL > 6) tail_step<TL, (TL > 6 ? 6 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
-      default: if (TL > 7) tail_step<TL, (TL > 7 ? 7 : 0)>(t, k, kr, ti, tj, pc, pr, flag); break;
+    switch (k >> 4) {   // uniform across the CTA
+      case 0: tail_step<TL, TC, 0>(t, k, ti, tj, pc, pr, flag, rdt); break;
+      case 1: if (TL > 1) tail_step<TL, TC, (TL > 1 ? 1 : 0)>(t, k, ti, tj, pc, pr, flag, rdt); break;
+      case 2: if (TL > 2) tail_step<TL, TC, (TL > 2 ? 2 : 0)>(t, k, ti, tj, pc, pr, flag, rdt); break;
+      case 3: if (TL > 3) tail_step<TL, TC, (TL > 3 ? 3 : 0)>(t, k, ti, tj, pc, pr, flag, rdt); break;
+      case 4: if (TL > 4) tail_step<TL, TC, (TL > 4 ? 4 : 0)>(t, k, ti, tj, pc, pr, flag, rdt); break;
+      case 5: if (TL > 5) tail_step<TL, TC, (TL > 5 ? 5 : 0)>(t, k, ti, tj, pc, pr, flag, rdt); break;
+      case 6: if (TL > 6) tail_step<TL, TC, (TL > 6 ? 6 : 0)>(t, k, ti, tj, pc, pr, flag, rdt); break;
+      default: if (TL > 7) tail_step<TL, TC, (TL > 7 ? 7 : 0)>(t, k, ti, tj, pc, pr, flag, rdt); break;
     }
   }
   __syncthreads();
 #pragma unroll
   for (int a = 0; a < TL; ++a)
 #pragma unroll
-    for (int b = 0; b < TL; ++b) Dt[(tj + 16 * b) * ldt + ti + 16 * a] = t[a][b];
-  __syncthreads();
-}
-
-// Replace every diagonal 32x32 block of the factored tail by the inverses of its unit-lower
-// and upper triangles (in place), so that the tail substitution becomes a few mat-vecs.
-// One thread per (block, triangle, column), the column of the inverse in registers.
-__device__ __noinline__ void tail_block_inverses(Smem sm, int ns) {
-  const DevNet& net = c_net;
-  const int nt = net.nt, ldt = net.ldt, nb = (nt + 31) >> 5;
-  const int job = threadIdx.x >> 5, j = threadIdx.x & 31;     // job = 2*block + (0: L, 1: U)
-  const int blk = job >> 1, upper = job & 1;
-  const int o = blk * 32;
-  const int bs = (nt - o) < 32 ? (nt - o) : 32;
-  const bool act = (job < 2 * nb) && (j < bs);
-  double z[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) z[i] = 0.0;
-  if (act) {
-    const double* D = sm.Dt + (o * ldt + o);
-    if (!upper) {
-      // unit lower: z_j = 1, z_i = -sum_{k=j}^{i-1} L(i,k) z_k
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i == j) z[i] = 1.0;
-        else if (i > j && i < bs) {
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k < 32; ++k) if (k < i && k >= j) s += D[k * ldt + i] * z[k];
-          z[i] = -s;
-        }
-      }
-    } else {
-      // upper with diagonal: z_j = 1/U_jj, z_i = -(sum_{k=i+1}^{j} U(i,k) z_k) / U_ii
-#pragma unroll
-      for (int i = 31; i >= 0; --i) {
-        if (i == j) z[i] = 1.0 / D[i * ldt + i];
-        else if (i < j) {
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k < 32; ++k) if (k > i && k <= j) s += D[k * ldt + i] * z[k];
-          z[i] = -s / D[i * ldt + i];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (act) {
-    double* D = sm.Dt + (o * ldt + o);
-    if (!upper) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) if (i > j && i < bs) D[j * ldt + i] = z[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) if (i <= j) D[j * ldt + i] = z[i];
-    }
-  }
+    for (int b = 0; b < TC; ++b) if (tj + TJ * b < nt) Dt[(tj + TJ * b) * ldt + ti + 16 * a] = t[a][b];
   __syncthreads();
 }
 
@@ -435,7 +406,7 @@ __device__ __noinline__ void tail_block_inverses(Smem sm, int ns) {
 // Shared-memory view of the level-parallel mode, derived from the smem_raw symbol so that
 // every access below is a shared-space access.
 struct GSm { double *y, *xb, *dinv, *V, *X, *Dt; const int4 *lvl, *grp, *st, *r1; };
-__device__ __forceinline__ GSm glu_smem(int ns) {
+__device__ __forceinline__ GSm glu_smem() {
   const DevNet& net = c_net;
   GSm g;
   g.y = smem_raw; g.xb = smem_raw + net.n; g.dinv = smem_raw + 2 * net.n;
@@ -444,93 +415,96 @@ __device__ __forceinline__ GSm glu_smem(int ns) {
   return g;
 }
 
-// Inverse of a triangular 32x32 block by one warp, column oriented: lane j owns column j of
-// the inverse in the scratch tile zs (zs[i*33 + j]); once z_k is final every remaining entry
-// of the column takes its update independently.  src is column-major with leading dimension
-// ld.  The L job (unit lower, result rows i > j) and the U job (result rows i <= j) of one
-// block share a scratch tile: their triangles are disjoint and the L job never touches the
-// diagonal (z_j = 1 is implicit).
-__device__ __forceinline__ void tri_inv_lower(const double* src, int ld, int bs, int j, double* zs) {
-  // rows in chunks of 8 held in registers: first the contributions of all earlier rows k
-  // (z_k final), then the 8x8 triangle of the chunk itself
-  for (int R0 = 0; R0 < bs; R0 += 8) {
-    double acc[8];
+// Triangular solves with a dense factored block (<= 128 rows) by ONE warp: plain substitution, as
+// the reference's nntc does (src/opkda1.f:3750-3801), organised as a column sweep with the
+// right-hand side in registers -- lane l owns row l of the current 32-row block (x0) and of the
+// three blocks that follow it in sweep direction (x1..x3) -- so that the dependent chain is one
+// shuffle and one FMA per column (forward) / one multiply by the stored reciprocal pivot more
+// (backward).  Operands are offsets into the shared-memory block: T column-major with leading
+// dimension ld, unit-lower L below and U on/above the diagonal; rd[i] = 1 / U(i,i); xs = the
+// vector, solved in place.  One compact loop body shared by every caller (not inlined): a single
+// warp runs this while the others wait, so its instruction fetches are fully exposed.
+// (Explicit inverses of the diagonal blocks were equally fast to apply but cost a factorisation
+// pass and lost the corrector on hot, very stiff cells: pivots spanning many decades.)
+// WIN = number of 32-row blocks in the register window (1: a single 32-row block, 4: nt <= 128)
+template <int WIN>
+__device__ __noinline__ void warp_trisolve_lower(int t_off, int ld, int nt, int xs_off) {
+  const double* const T = smem_raw + t_off;
+  double* const xs = smem_raw + xs_off;
+  const int l = threadIdx.x & 31, nb = (nt + 31) >> 5;
+  double x[WIN];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.0;
-    for (int k = 0; k < R0; ++k) {
-      const double zl = zs[k * 33 + j];
-      const double zk = (k < j) ? 0.0 : ((k == j) ? 1.0 : zl);
-      const double* lk = src + k * ld + R0;
+  for (int m = 0; m < WIN; ++m) x[m] = (32 * m + l < nt) ? xs[32 * m + l] : 0.0;
+#pragma unroll 1
+  for (int mb = 0; mb < nb; ++mb) {
+    const int base = 32 * mb, cmax = (nt - base) < 32 ? (nt - base) : 32;
+    bool on[WIN];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) acc[r] -= lk[r] * zk;
+    for (int m = 0; m < WIN; ++m) on[m] = base + 32 * m + l < nt;
+    const double* col = T + base * ld + base + l;
+#pragma unroll 1
+    for (int c0 = 0; c0 < cmax; c0 += 8) {
+      double a[WIN][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[0][j] = (on[0] && l > c0 + j) ? col[j * ld] : 0.0;
+#pragma unroll
+        for (int m = 1; m < WIN; ++m) a[m][j] = on[m] ? col[j * ld + 32 * m] : 0.0;
+      }
+      col += 8 * ld;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double xc = __shfl_sync(0xffffffffu, x[0], c0 + j);
+#pragma unroll
+        for (int m = 0; m < WIN; ++m) x[m] -= a[m][j] * xc;
+      }
     }
-    double z[8];
+    if (on[0]) xs[base + l] = x[0];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int i = R0 + r;
-      double v = acc[r];
-#pragma unroll
-      for (int r2 = 0; r2 < r; ++r2) v -= src[(R0 + r2) * ld + i] * z[r2];
-      z[r] = (i < j) ? 0.0 : ((i == j) ? 1.0 : v);
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) if (R0 + r > j) zs[(R0 + r) * 33 + j] = z[r];
+    for (int m = 0; m + 1 < WIN; ++m) x[m] = x[m + 1];
+    x[WIN - 1] = 0.0;
   }
 }
-__device__ __forceinline__ void tri_inv_upper(const double* src, int ld, int bs, int j, double* zs) {
-  const double rd = (j < bs) ? 1.0 / src[j * ld + j] : 1.0;   // lane j: reciprocal of pivot j
-  for (int R0 = bs - 8; R0 >= 0; R0 -= 8) {
-    double acc[8];
+template <int WIN>
+__device__ __noinline__ void warp_trisolve_upper(int t_off, int ld, int nt, int rd_off, int xs_off) {
+  const double* const T = smem_raw + t_off;
+  const double* const rd = smem_raw + rd_off;
+  double* const xs = smem_raw + xs_off;
+  const int l = threadIdx.x & 31, nb = (nt + 31) >> 5;
+  const int top = 32 * (nb - 1);
+  double x[WIN];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.0;
-    for (int k = bs - 1; k >= R0 + 8; --k) {
-      const double zl = zs[k * 33 + j];
-      const double zk = (k > j) ? 0.0 : zl;
-      const double* uk = src + k * ld + R0;
+  for (int m = 0; m < WIN; ++m) x[m] = (m < nb && top - 32 * m + l < nt) ? xs[top - 32 * m + l] : 0.0;
+#pragma unroll 1
+  for (int mb = nb - 1; mb >= 0; --mb) {
+    const int base = 32 * mb, cmax = (nt - base) < 32 ? (nt - base) : 32;
+    // the current block is carried scaled by its reciprocal pivots, s_r = x_r / U(r,r), and so are
+    // its U entries: lane c then holds the finished x_c when column c is reached, and the chain is
+    // shuffle + FMA as in the forward sweep
+    const double rdl = (base + l < nt) ? rd[base + l] : 1.0;
+    x[0] *= rdl;
+    const double* col = T + (base + cmax - 8) * ld + base + l;
+#pragma unroll 1
+    for (int c0 = cmax - 8; c0 >= 0; c0 -= 8) {
+      double a[WIN][8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) acc[r] -= uk[r] * zk;
+      for (int j = 0; j < 8; ++j) {
+        a[0][j] = (l < c0 + j) ? col[j * ld] * rdl : 0.0;
+#pragma unroll
+        for (int m = 1; m < WIN; ++m) a[m][j] = (mb >= m) ? col[j * ld - 32 * m] : 0.0;
+      }
+      col -= 8 * ld;
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        const double xc = __shfl_sync(0xffffffffu, x[0], c0 + j);
+#pragma unroll
+        for (int m = 0; m < WIN; ++m) x[m] -= a[m][j] * xc;
+      }
     }
-    double z[8];
+    if (base + l < nt) xs[base + l] = x[0];
 #pragma unroll
-    for (int r = 7; r >= 0; --r) {
-      const int i = R0 + r;
-      double v = acc[r] + ((i == j) ? 1.0 : 0.0);
-#pragma unroll
-      for (int r2 = r + 1; r2 < 8; ++r2) v -= src[(R0 + r2) * ld + i] * z[r2];
-      const double ri = __shfl_sync(0xffffffffu, rd, i);
-      z[r] = (i > j) ? 0.0 : v * ri;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) if (R0 + r <= j) zs[(R0 + r) * 33 + j] = z[r];
-  }
-}
-
-// Inverses of all diagonal 32-blocks used by the staged solves, in place: the S blocks of the
-// head (dense copies at X + sinv, ld 33) and the blocks of the dense tail (ld ldt).  After the
-// call the strictly-lower part of a block holds L^-1 (unit diagonal implicit) and the upper
-// part U^-1.  One warp per job, two jobs (L, U) per block, scratch = NW/2 tiles at X.
-__device__ __noinline__ void block_inverses(int subst, int ns) {
-  const DevNet& net = c_net;
-  const GSm sm = glu_smem(ns);
-  const int nt = net.nt, ldt = net.ldt, nbT = (nt + 31) >> 5, nbS = net.ss.nblkS;
-  const int w = threadIdx.x >> 5, j = threadIdx.x & 31;
-  double* zs = sm.X + (w >> 1) * (33 * 32);
-  for (int job0 = 0; job0 < 2 * (nbS + nbT); job0 += NW) {
-    const int job = job0 + w, blk = job >> 1, upper = job & 1;
-    const int sbit = upper ? ((job >> 1) < nbS ? 8 : 2) : 1;
-    const bool act = job < 2 * (nbS + nbT) && !(subst & sbit);   // triangles solved by substitution stay as they are
-    double* D = sm.X; int ld = 33, bs = 32;
-    if (act) {
-      if (blk < nbS) D = sm.X + net.ss.sinv + blk * (33 * 32);
-      else { const int o = (blk - nbS) * 32; D = sm.Dt + (o * ldt + o); ld = ldt; bs = (nt - o) < 32 ? (nt - o) : 32; }
-      if (upper) tri_inv_upper(D, ld, bs, j, zs); else tri_inv_lower(D, ld, bs, j, zs);
-    }
-    __syncthreads();   // both jobs of every block have read their triangle
-    if (act && j < bs) {
-      if (!upper) { for (int i = j + 1; i < bs; ++i) D[j * ld + i] = zs[i * 33 + j]; }
-      else { for (int i = 0; i <= j; ++i) D[j * ld + i] = zs[i * 33 + j]; }
-    }
-    __syncthreads();
+    for (int m = 0; m + 1 < WIN; ++m) x[m] = x[m + 1];
+    x[WIN - 1] = 0.0;
   }
 }
 
@@ -568,15 +542,15 @@ __device__ __forceinline__ void glu_group(const uint32_t* __restrict__ ep, const
 
 // P = I - hl0*J and its LU, level-parallel ("gather") formulation: see HostNet::LevelLU.
 // The whole factor V (storage order) is in shared memory.  Returns 0 ok / 1 zero pivot.
-__device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned long long* ph, int subst, int ns) {
-  const GSm sm = glu_smem(ns);
+__device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned long long* ph) {
+  const GSm sm = glu_smem();
   const DevNet& net = c_net;
   const GluDev& g = net.glu;
   const int nh = net.nh, nt = net.nt, ldt = net.ldt;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, tid = threadIdx.x;
   double* V = sm.V;
   if (tid == 0) *flag = 0;
-  const long long t0 = clock64();
+  const long long t0 = pclock();
   {
     const double2* J2 = (const double2*)ws.J;
     double2* V2 = (double2*)V;
@@ -592,7 +566,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
   for (int i = tid; i < nh; i += NT) V[__ldg(net.pivmeta + i).x - 1] += 1.0;
   for (int a = tid; a < nt; a += NT) sm.Dt[a * ldt + a] += 1.0;
   __syncthreads();
-  const long long t0b = clock64();
+  const long long t0b = pclock();
   const uint32_t ZZ = (uint32_t)g.zpos | ((uint32_t)g.zpos << 16);
   const int zp = g.zpos;
   // index entries of the next level's pivot/multiplier phase are fetched one level ahead
@@ -604,7 +578,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
     m1 = (L0.y + tid + NT < L1.y) ? __ldg(g.mul + L0.y + tid + NT) : ZZ;
   }
   for (int lev = 0; lev < g.nlev; ++lev) {
-    const long long tlev = clock64();
+    const long long tlev = pclock();
     const int4 L0 = sm.lvl[lev], L1 = sm.lvl[lev + 1];
     // rank-1 level: the first target chunk pair and the first multiplier position of this warp
     // are requested now and land during the multiplier phase
@@ -643,7 +617,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
       V[e & 0xffffu] = V[e & 0xffffu] / V[e >> 16];
     }
     __syncthreads();
-    long long tq = clock64();
+    long long tq = pclock();
     if (tid == 0) ph[PH_G_PIVMUL] += tq - tlev;
     if (lev + 1 < g.nlev) {
       const int4 L2 = sm.lvl[lev + 2];
@@ -701,7 +675,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
         fresh = nrc != rc;
         ca = na; cb = nb2; lpc = lpn; rc = nrc; j4 = nj; have = hnext;
       }
-      if (tid == 0) { const long long tn2 = clock64(); ph[PH_G_FLAT] += tn2 - tq; tq = tn2; }
+      if (tid == 0) { const long long tn2 = pclock(); ph[PH_G_FLAT] += tn2 - tq; tq = tn2; }
     }
     int rot = 0;
     for (int gi = L0.z; gi < L1.z; ++gi) {
@@ -748,18 +722,18 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
           if (t != 0xFFFFu) V[t] -= (acc[0] + acc[1]) + (acc[2] + acc[3]);
         }
       }
-      if (tid == 0) { const long long tn2 = clock64(); ph[G.x == 1 ? PH_G_FLAT : (G.x <= 8 ? PH_G_NARROW : PH_G_WIDE)] += tn2 - tq; tq = tn2; }
+      if (tid == 0) { const long long tn2 = pclock(); ph[G.x == 1 ? PH_G_FLAT : (G.x <= 8 ? PH_G_NARROW : PH_G_WIDE)] += tn2 - tq; tq = tn2; }
     }
     __syncthreads();
-    if (tid == 0) ph[PH_G_PIVMUL] += clock64() - tq;
+    if (tid == 0) ph[PH_G_PIVMUL] += pclock() - tq;
   }
-  const long long t1 = clock64();
+  const long long t1 = pclock();
   // ---- U_B / L_C in ELL order for the solves
   for (int q = tid; q < net.n_ub; q += NT) ws.ubE[__ldg(net.ub_ellpos + q)] = V[net.o_ub + q];
   for (int q = tid; q < net.n_lc; q += NT) ws.lcE[__ldg(net.lc_ellpos + q)] = V[net.o_lc + q];
   __syncthreads();   // X (= the U_B/L_C part of V) is scratch from here on
-  if (tid == 0) { ph[PH_G_COPY] += clock64() - t1; ph[PH_G_LOOP] += t1 - t0b; }
-  const long long t2 = clock64();
+  if (tid == 0) { ph[PH_G_COPY] += pclock() - t1; ph[PH_G_LOOP] += t1 - t0b; }
+  const long long t2 = pclock();
   // ---- tables of the staged solves and dense copies of the S diagonal blocks -> upper part of X
   {
     uint32_t* tab = (uint32_t*)(sm.X + net.ss.tab);
@@ -776,17 +750,16 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
   // ---- dense tail
   const int dto = (int)(sm.Dt - smem_raw), pbo = (int)(sm.X - smem_raw);
   switch (nt >> 4) {
-    case 1: tail_lu<1>(dto, pbo, flag, ns); break; case 2: tail_lu<2>(dto, pbo, flag, ns); break;
-    case 3: tail_lu<3>(dto, pbo, flag, ns); break; case 4: tail_lu<4>(dto, pbo, flag, ns); break;
-    case 5: tail_lu<5>(dto, pbo, flag, ns); break; case 6: tail_lu<6>(dto, pbo, flag, ns); break;
-    case 7: tail_lu<7>(dto, pbo, flag, ns); break; default: tail_lu<8>(dto, pbo, flag, ns); break;
+    case 1: tail_lu<1>(dto, pbo, flag); break; case 2: tail_lu<2>(dto, pbo, flag); break;
+    case 3: tail_lu<3>(dto, pbo, flag); break; case 4: tail_lu<4>(dto, pbo, flag); break;
+    case 5: tail_lu<5>(dto, pbo, flag); break; case 6: tail_lu<6>(dto, pbo, flag); break;
+    case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
   }
-  const long long t2b = clock64();
-  if ((subst & 11) != 11) block_inverses(subst, ns);
+  const long long t2b = pclock();
   const int res = *flag;
   __syncthreads();
   if (tid == 0) {
-    const long long t3 = clock64();
+    const long long t3 = pclock();
     ph[PH_FACT_HEAD] += t1 - t0; ph[PH_FACT_SCHUR] += t2 - t1; ph[PH_FACT_TAIL] += t3 - t2;
     ph[PH_PBUILD] += t0b - t0; ph[PH_TAILINV] += t3 - t2b;
   }
@@ -796,7 +769,7 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
 // P = I - hl0*J (WK = J*CON, +1 on the diagonal; src/opkda1.f:1763-1764) and its numeric LU.
 // Returns (to all threads) 0 ok / 1 zero pivot.
 template <bool ALLSMEM>
-__device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, int* flag, unsigned long long* ph, int ns) {
+__device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, int* flag, unsigned long long* ph) {
   const DevNet& net = c_net;
   const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, tid = threadIdx.x;
@@ -806,7 +779,7 @@ __device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, in
   double* ub = (ALLSMEM || lay.ub_smem) ? sm.X + NWR * n : ws.ubG;
   const uint16_t* ubcol = (ALLSMEM || lay.ub_smem) ? (const uint16_t*)(sm.X + NWR * n + net.n_ub) : net.ub_col;
   if (tid == 0) *flag = 0;
-  long long t0 = clock64();
+  long long t0 = pclock();
   // ---- build P
   for (int s = tid; s < net.n_hh; s += NT) sm.hh[s] = __ldcs(ws.J + s) * con;
   for (int s = tid; s < net.n_ub; s += NT) ub[s] = __ldcs(ws.J + net.o_ub + s) * con;
@@ -819,7 +792,7 @@ __device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, in
   for (int i = tid; i < nh; i += NT) sm.hh[__ldg(net.pivmeta + i).x - 1] += 1.0;
   for (int a = tid; a < nt; a += NT) sm.Dt[a * ldt + a] += 1.0;
   __syncthreads();
-  long long t0b = clock64();
+  long long t0b = pclock();
   // ---- head rows, level by level, one warp per row (up-looking through a dense work row over
   // all n columns).  The pivots k of a row and their metadata are fetched 32 at a time (one
   // lane each) so that the sequential k-loop touches shared memory only.
@@ -869,7 +842,7 @@ __device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, in
     }
     __syncthreads();
   }
-  long long t1 = clock64();
+  long long t1 = pclock();
   // ---- tail rows against the head pivots (rows are independent; longest first):
   // multipliers L_C(a,:) -> ELL copy for the solves, Schur row -> Dt
   for (int ai = w; ai < nt && w < NWR; ai += NWR) {
@@ -905,21 +878,20 @@ __device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, in
   for (int s = tid; s < net.n_ub; s += NT) ws.ubE[__ldg(net.ub_ellpos + s)] = ub[s];
   __syncthreads();   // X (work rows, U_B) is reused as scratch by the dense tail below
   if (!lay.hh_smem) __threadfence_block();
-  long long t2 = clock64();
+  long long t2 = pclock();
   // ---- dense tail
   const int dto = (int)(sm.Dt - smem_raw), pbo = (int)(sm.X - smem_raw);
   switch (nt >> 4) {
-    case 1: tail_lu<1>(dto, pbo, flag, ns); break; case 2: tail_lu<2>(dto, pbo, flag, ns); break;
-    case 3: tail_lu<3>(dto, pbo, flag, ns); break; case 4: tail_lu<4>(dto, pbo, flag, ns); break;
-    case 5: tail_lu<5>(dto, pbo, flag, ns); break; case 6: tail_lu<6>(dto, pbo, flag, ns); break;
-    case 7: tail_lu<7>(dto, pbo, flag, ns); break; default: tail_lu<8>(dto, pbo, flag, ns); break;
+    case 1: tail_lu<1>(dto, pbo, flag); break; case 2: tail_lu<2>(dto, pbo, flag); break;
+    case 3: tail_lu<3>(dto, pbo, flag); break; case 4: tail_lu<4>(dto, pbo, flag); break;
+    case 5: tail_lu<5>(dto, pbo, flag); break; case 6: tail_lu<6>(dto, pbo, flag); break;
+    case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
   }
-  long long t2b = clock64();
-  tail_block_inverses(sm, ns);
+  long long t2b = pclock();
   const int res = *flag;
   __syncthreads();
   if (tid == 0) {
-    long long t3 = clock64();
+    long long t3 = pclock();
     ph[PH_FACT_HEAD] += t1 - t0; ph[PH_FACT_SCHUR] += t2 - t1; ph[PH_FACT_TAIL] += t3 - t2;
     ph[PH_PBUILD] += t0b - t0; ph[PH_TAILINV] += t3 - t2b;
   }
@@ -958,64 +930,15 @@ __device__ __forceinline__ void spmv_sub(const EllDev& e, const double* __restri
 
 // DSOLSS for the level-parallel mode: staged head sweeps (HostNet::SolveSched, tables in
 // shared memory), SpMVs with the coupling blocks whose values are fetched into registers
-// one phase ahead, blocked dense tail solve on all warps.
+// one phase ahead; the diagonal blocks of the S rows and the dense tail are solved by plain
+// substitution on warp 0 (warp_trisolve).
 __device__ __forceinline__ double group_sum(double v, int lpr) {
   for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// x_blk <- T^-1-part applied to tmp for a 32-row block whose inverse sits in place (column-major,
-// ld): lower: x_r = tmp_r + sum_{c<r} T(r,c) tmp_c; upper: x_r = sum_{c>=r} T(r,c) tmp_c.
-// Thread (r, sg) = (tid / 8, tid % 8); returns the row's value in lane sg == 0.
-__device__ __forceinline__ double block_apply(const double* T, int ld, int bs, bool upper, const double* tmp, int r, int sg) {
-  double mv = 0.0;
-  if (r < bs) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = sg + 8 * j;
-      const bool on = upper ? (c >= r && c < bs) : (c < r);
-      if (on) mv += T[c * ld + r] * tmp[c];
-    }
-  }
-  mv = group_sum(mv, 8);
-  return upper ? mv : mv + tmp[r < 32 ? r : 0];
-}
-
-// in-block triangular substitution by one warp (lane r owns row r); T column-major, ld.
-// The lane's row of the triangle is fetched into registers first, so that the 32 dependent
-// steps are one shuffle and one FMA each.  Used for the U blocks: their explicit inverses
-// mix pivots of very different size and cost the hottest cells (T > 1700 K) their
-// convergence (78 k instead of 1.8 k steps were measured); L blocks keep the inverses.
-__device__ __forceinline__ double block_subst(const double* T, int ld, int bs, bool upper, double v, int r) {
-  if (!upper) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      double row[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { const int c = 16 * h + q; row[q] = (c < r && r < bs) ? T[c * ld + r] : 0.0; }
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { const double xc = __shfl_sync(0xffffffffu, v, 16 * h + q); v -= row[q] * xc; }
-    }
-  } else {
-    const double rd = (r < bs) ? 1.0 / T[r * ld + r] : 1.0;
-#pragma unroll
-    for (int h = 1; h >= 0; --h) {
-      double row[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { const int c = 16 * h + q; row[q] = (c > r && c < bs) ? T[c * ld + r] : 0.0; }
-#pragma unroll
-      for (int q = 15; q >= 0; --q) {
-        if (r == 16 * h + q) v = v * rd;
-        const double xc = __shfl_sync(0xffffffffu, v, 16 * h + q);
-        v -= row[q] * xc;
-      }
-    }
-  }
-  return v;
-}
-
 __device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const uint32_t* ent, const uint16_t* rp,
-                                           const uint16_t* rows, double* tmp, bool upper, int subst, int ns) {
+                                           const uint16_t* rows, double* tmp, bool upper) {
   const DevNet& net = c_net;
   const int tid = threadIdx.x;
   const int kind = S.x & 255, lg = (S.x >> 8) & 255, lpr = 1 << lg, nrows = S.y & 0xffff, blk = S.y >> 16;
@@ -1042,28 +965,32 @@ __device__ __forceinline__ void head_stage(const int4 S, const GSm& sm, const ui
     __syncthreads();
     return;
   }
+  // S block: the rows' coupling inside the 32-row diagonal block (dense copy at X + sinv, ld 33,
+  // identity-padded) is resolved by substitution on warp 0
   if (sub == 0) tmp[r] = (r < nrows) ? sm.xb[row] - acc : 0.0;
   __syncthreads();
-  if (subst & (upper ? 8 : 1)) {
-    if (tid < 32) {
-      const double xv = block_subst(sm.X + net.ss.sinv + blk * (33 * 32), 33, 32, upper, tmp[tid], tid);
-      if (tid < nrows) sm.xb[rows[S.z + tid]] = xv;
-    }
-    __syncthreads();
-    return;
+  if (tid < 32) {
+    const int t_off = (int)(sm.X - smem_raw) + net.ss.sinv + blk * (33 * 32), tmp_off = (int)(tmp - smem_raw);
+    const int myrow = (tid < nrows) ? (int)rows[S.z + tid] : 0;
+    if (upper) {
+      tmp[32 + tid] = (tid < nrows) ? sm.dinv[myrow] : 1.0;     // reciprocal pivots of the block's rows
+      __syncwarp();
+      warp_trisolve_upper<1>(t_off, 33, 32, tmp_off + 32, tmp_off);
+    } else warp_trisolve_lower<1>(t_off, 33, 32, tmp_off);
+    __syncwarp();
+    if (tid < nrows) sm.xb[myrow] = tmp[tid];
   }
-  const double xv = block_apply(sm.X + net.ss.sinv + blk * (33 * 32), 33, 32, upper, tmp, r, sub);
-  if (sub == 0 && r < nrows) sm.xb[row] = xv;
   __syncthreads();
 }
 
 // coupling-block SpMV, split in two so that the loads fly while other phases run:
-// each warp owns blocks w and w + NW of the ELL copy (<= 16 entries per sub-row)
-struct EllRegs { double v[2][16]; uint32_t c[2][8]; };
-__device__ __forceinline__ void ell_fetch(const EllDev& e, const double* __restrict__ val, EllRegs& R) {
+// each warp owns blocks w (and w + NW when U = 2) of the ELL copy (<= 16 entries per sub-row)
+template <int U> struct EllRegs { double v[U][16]; uint32_t c[U][8]; };
+template <int U>
+__device__ __forceinline__ void ell_fetch(const EllDev& e, const double* __restrict__ val, EllRegs<U>& R) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < U; ++u) {
     const int b = w + u * NW;
     const bool on = b < e.nblk;
     const int off = on ? __ldg(e.blk_off + b) : 0, width = on ? __ldg(e.blk_width + b) : 0;
@@ -1077,10 +1004,11 @@ __device__ __forceinline__ void ell_fetch(const EllDev& e, const double* __restr
     }
   }
 }
-__device__ __forceinline__ void ell_apply(const EllDev& e, const EllRegs& R, const double* x, double* out, double* partial) {
+template <int U>
+__device__ __forceinline__ void ell_apply(const EllDev& e, const EllRegs<U>& R, const double* x, double* out, double* partial) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < U; ++u) {
     const int b = w + u * NW;
     if (b < e.nblk) {
       double a0 = 0.0, a1 = 0.0;
@@ -1103,82 +1031,44 @@ __device__ __forceinline__ void ell_apply(const EllDev& e, const EllRegs& R, con
   __syncthreads();
 }
 
-__device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst, int ns) {
+template <int U>
+__device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
   const DevNet& net = c_net;
-  const GSm sm = glu_smem(ns);
+  const GSm sm = glu_smem();
   const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
   const int tid = threadIdx.x;
-  double* tmp = sm.X;            // [32] block right-hand side; the SpMV partials start behind it
-  double* part = sm.X + 32;
+  double* tmp = sm.X;            // [64] block right-hand side + reciprocal pivots; the SpMV partials start behind
+  double* part = sm.X + 64;
   const uint32_t* ent = (const uint32_t*)(sm.X + net.ss.tab);
   const uint16_t* rp = (const uint16_t*)(ent + net.ss.nent);
   const uint16_t* rows = rp + ((net.ss.nrp + 1) & ~1);
-  const long long t0 = clock64();
-  EllRegs R;
+  const long long t0 = pclock();
+  EllRegs<U> R;
   ell_fetch(net.lcE, ws.lcE, R);           // lands while the head sweep runs
   for (int i = tid; i < n; i += NT) sm.xb[i] = sm.y[__ldg(net.perm + i)];
   __syncthreads();
-  for (int st = 0; st < net.ss.nf; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, false, subst, ns);
-  const long long t1 = clock64();
+  for (int st = 0; st < net.ss.nf; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, false);
+  const long long t1 = pclock();
   // ---- tail right-hand side: x_T -= L_C x_H
   ell_apply(net.lcE, R, sm.xb, sm.xb + nh, part);
   ell_fetch(net.ubE, ws.ubE, R);           // lands while the tail is solved
-  const long long t1b = clock64();
-  // ---- dense tail, 32-row blocks: thread (r, sg) = (tid / 8, tid % 8)
-  {
-    double* xt = sm.xb + nh;
-    const int nbT = (nt + 31) >> 5;
-    const int r = tid >> 3, sg = tid & 7;
-    for (int m = 0; m < nbT; ++m) {          // forward, unit lower; diagonal blocks hold L^-1
-      const int o = 32 * m, bs = (nt - o) < 32 ? (nt - o) : 32, row = o + r;
-      double a0 = 0.0, a1 = 0.0;
-      if (r < bs) {
-        for (int c = sg; c < o; c += 16) {
-          a0 += sm.Dt[c * ldt + row] * xt[c];
-          if (c + 8 < o) a1 += sm.Dt[(c + 8) * ldt + row] * xt[c + 8];
-        }
-      }
-      const double acc = group_sum(a0 + a1, 8);
-      if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
-      __syncthreads();
-      if (subst & 1) {
-        if (tid < 32) { const double xv = block_subst(sm.Dt + (o * ldt + o), ldt, bs, false, tmp[tid], tid); if (tid < bs) xt[o + tid] = xv; }
-      } else {
-        const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, false, tmp, r, sg);
-        if (sg == 0 && r < bs) xt[row] = xv;
-      }
-      __syncthreads();
-    }
-    for (int m = nbT - 1; m >= 0; --m) {     // backward, upper; diagonal blocks hold U^-1
-      const int o = 32 * m, bs = (nt - o) < 32 ? (nt - o) : 32, row = o + r;
-      double a0 = 0.0, a1 = 0.0;
-      if (r < bs) {
-        for (int c = o + bs + sg; c < nt; c += 16) {
-          a0 += sm.Dt[c * ldt + row] * xt[c];
-          if (c + 8 < nt) a1 += sm.Dt[(c + 8) * ldt + row] * xt[c + 8];
-        }
-      }
-      const double acc = group_sum(a0 + a1, 8);
-      if (sg == 0) tmp[r] = (r < bs) ? xt[row] - acc : 0.0;
-      __syncthreads();
-      if (subst & 2) {
-        if (tid < 32) { const double xv = block_subst(sm.Dt + (o * ldt + o), ldt, bs, true, tmp[tid], tid); if (tid < bs) xt[o + tid] = xv; }
-      } else {
-        const double xv = block_apply(sm.Dt + (o * ldt + o), ldt, bs, true, tmp, r, sg);
-        if (sg == 0 && r < bs) xt[row] = xv;
-      }
-      __syncthreads();
-    }
+  const long long t1b = pclock();
+  // ---- dense tail: forward and backward substitution on warp 0
+  if (tid < 32) {
+    const int dto = (int)(sm.Dt - smem_raw), xo = (int)(sm.xb - smem_raw) + nh;
+    warp_trisolve_lower<4>(dto, ldt, nt, xo);
+    warp_trisolve_upper<4>(dto, ldt, nt, (int)(sm.dinv - smem_raw) + nh, xo);
   }
-  const long long t1c = clock64();
+  __syncthreads();
+  const long long t1c = pclock();
   // ---- head right-hand side: x_H -= U_B x_T
   ell_apply(net.ubE, R, sm.xb + nh, sm.xb, part);
-  const long long t2 = clock64();
-  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, true, subst, ns);
+  const long long t2 = pclock();
+  for (int st = net.ss.nf; st < net.ss.nf + net.ss.nb; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, true);
   for (int i = tid; i < n; i += NT) sm.y[__ldg(net.perm + i)] = sm.xb[i];
   __syncthreads();
   if (tid == 0) {
-    const long long t3 = clock64();
+    const long long t3 = pclock();
     ph[PH_S_FWD] += t1 - t0; ph[PH_S_TAIL] += t2 - t1; ph[PH_S_BWD] += t3 - t2;
     ph[PH_S_SPMV] += (t1b - t1) + (t2 - t1c);
   }
@@ -1186,7 +1076,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph, int subst,
 
 // DSOLSS: sm.y <- P^{-1} sm.y (original species order in, original order out)
 // (wiped: P is pw*I, see DPRJS below)
-__device__ __forceinline__ void solve(Ws ws, Smem sm, bool wiped, double pw, int ns) {
+__device__ __forceinline__ void solve(Ws ws, Smem sm, bool wiped, double pw) {
   const DevNet& net = c_net;
   const int n = net.n, nh = net.nh, nt = net.nt, ldt = net.ldt;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, tid = threadIdx.x;
@@ -1224,64 +1114,11 @@ __device__ __forceinline__ void solve(Ws ws, Smem sm, bool wiped, double pw, int
   __syncthreads();
   // ---- tail right-hand side: x_T -= L_C x_H
   spmv_sub(net.lcE, ws.lcE, sm.xb, sm.xb + nh, sm.X);
-  // ---- dense tail by one warp: x in registers, 32-blocks, inverted diagonal blocks
+  // ---- dense tail: forward and backward substitution on warp 0
   if (w == 0) {
-    const int nb = (nt + 31) >> 5;
-    double x[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) x[m] = (m < nb && 32 * m + l < nt) ? sm.xb[nh + 32 * m + l] : 0.0;
-    // forward: unit lower
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (m < nb) {
-        const int r = 32 * m + l;
-        const bool valid = r < nt;
-        double a0 = x[m], a1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const double x0 = __shfl_sync(0xffffffffu, x[m], j), x1 = __shfl_sync(0xffffffffu, x[m], j + 1);
-          if (valid && j < l && 32 * m + j < nt) a0 += sm.Dt[(size_t)(32 * m + j) * ldt + r] * x0;
-          if (valid && j + 1 < l && 32 * m + j + 1 < nt) a1 += sm.Dt[(size_t)(32 * m + j + 1) * ldt + r] * x1;
-        }
-        x[m] = a0 + a1;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const double xj = __shfl_sync(0xffffffffu, x[m], j);
-          if (32 * m + j < nt) {
-#pragma unroll
-            for (int mm = 0; mm < 4; ++mm)
-              if (mm > m && mm < nb && 32 * mm + l < nt) x[mm] -= sm.Dt[(size_t)(32 * m + j) * ldt + 32 * mm + l] * xj;
-          }
-        }
-      }
-    }
-    // backward: upper, diagonal blocks hold U^{-1}
-#pragma unroll
-    for (int m = 3; m >= 0; --m) {
-      if (m < nb) {
-        const int r = 32 * m + l;
-        const bool valid = r < nt;
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const double x0 = __shfl_sync(0xffffffffu, x[m], j), x1 = __shfl_sync(0xffffffffu, x[m], j + 1);
-          if (valid && j >= l && 32 * m + j < nt) a0 += sm.Dt[(size_t)(32 * m + j) * ldt + r] * x0;
-          if (valid && j + 1 >= l && 32 * m + j + 1 < nt) a1 += sm.Dt[(size_t)(32 * m + j + 1) * ldt + r] * x1;
-        }
-        x[m] = a0 + a1;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const double xj = __shfl_sync(0xffffffffu, x[m], j);
-          if (32 * m + j < nt) {
-#pragma unroll
-            for (int mm = 0; mm < 4; ++mm)
-              if (mm < m && 32 * mm + l < nt) x[mm] -= sm.Dt[(size_t)(32 * m + j) * ldt + 32 * mm + l] * xj;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) if (m < nb && 32 * m + l < nt) sm.xb[nh + 32 * m + l] = x[m];
+    const int dto = (int)(sm.Dt - smem_raw), xo = (int)(sm.xb - smem_raw) + nh;
+    warp_trisolve_lower<4>(dto, ldt, nt, xo);
+    warp_trisolve_upper<4>(dto, ldt, nt, (int)(sm.dinv - smem_raw) + nh, xo);
   }
   __syncthreads();
   // ---- head right-hand side: x_H -= U_B x_T
@@ -1338,7 +1175,6 @@ struct Lsodes {      // COMMON /DLS001/ + /DLSS01/ (uniform across the CTA, held
 template <int EPT, bool GLU>
 __global__ void __launch_bounds__(NT, 1)
 integrate_kernel(const BatchArgs args) {
-  const int ns = args.net_slot;
   const DevNet& net = c_net;
   __shared__ int s_cell, s_flag;
   __shared__ unsigned long long s_ph[PH_COUNT];   // per-phase cycle counters (thread 0 only)
@@ -1355,7 +1191,7 @@ integrate_kernel(const BatchArgs args) {
   Smem sm;
   if (GLU) {
     double* p = smem_raw;
-    sm.y = p; p += n; sm.savf = p; p += n; sm.xb = sm.savf; sm.dinv = p; p += net.nh;
+    sm.y = p; p += n; sm.savf = p; p += n; sm.xb = sm.savf; sm.dinv = p; p += n;
     sm.par = p; p += 32; sm.red = p;
     double* V = smem_raw + lay.voff;      // the factor in storage order: [hh | U_B | L_C | tail]
     sm.hh = V; sm.X = V + net.o_ub; sm.Dt = V + net.o_tl;
@@ -1364,7 +1200,7 @@ integrate_kernel(const BatchArgs args) {
     for (int q = tid; q < net.glu.ndesc; q += NT) dsc[q] = net.glu.desc[q];
   } else {
     double* p = smem_raw;
-    sm.y = p; p += n; sm.savf = p; p += n; sm.xb = sm.savf; sm.dinv = p; p += net.nh;
+    sm.y = p; p += n; sm.savf = p; p += n; sm.xb = sm.savf; sm.dinv = p; p += n;
     sm.par = p; p += 32; sm.red = p; p += 2 * NW; sm.Dt = p; p += (size_t)net.ldt * net.nt;
     if (lay.hh_smem) { sm.hh = p; p += net.n_hh; } else sm.hh = ws.hhG;
     // index tables (staged below, once per CTA)
@@ -1383,6 +1219,7 @@ integrate_kernel(const BatchArgs args) {
     sm.X = p;
   }
   const int x_off = (int)(sm.X - smem_raw);   // scratch region: fluxes [R] | gather partials
+  const bool ell1 = net.ubE.nblk <= NW && net.lcE.nblk <= NW;   // one ELL block per warp in the solves' SpMVs
   const double* ks = ws.ksave;
   unsigned long long* const ph = s_ph;
   if (tid < PH_COUNT) s_ph[tid] = 0;
@@ -1392,15 +1229,13 @@ integrate_kernel(const BatchArgs args) {
   // element e of this thread is species i = tid + e*NT
   double yh[EPT][6], acor[EPT], ewt[EPT], rt[EPT], at[EPT];
 #define FORE _Pragma("unroll") for (int e = 0, i = tid; e < EPT; ++e, i += NT) if (i < n)
-  int redo_mask = -1;   // >= 0: integrate the same cell again with this block-solve mode
-  long long cNST = 0, cNFE = 0, cNJE = 0, cNLU = 0, cSOL = 0, cCF = 0, cEF = 0;   // work of the abandoned attempt
   for (;;) {
     __syncthreads();
-    if (tid == 0 && redo_mask < 0) s_cell = atomicAdd(args.queue, 1);
+    if (tid == 0) s_cell = atomicAdd(args.queue, 1);
     __syncthreads();
     if (s_cell >= ncell) break;
     const int cell = args.order ? args.order[s_cell] : s_cell;
-    long long tc = clock64();
+    long long tc = pclock();
     // ---- load the cell
     if (tid < RACG_NPAR) sm.par[tid] = args.cellpar[(size_t)tid * ncell + cell];
     FORE sm.y[i] = args.y0[(size_t)i * ncell + cell];
@@ -1446,20 +1281,20 @@ integrate_kernel(const BatchArgs args) {
       for (int d = tid; d < net.ndup; d += NT) resolve_dupli(net, cc.Tgas, d, [&](int z) { ws.ksave[z] = 0.0; });
       __syncthreads();
     }
-    if (tid == 0) { long long t = clock64(); ph[PH_RATES] += t - tc; }
+    if (tid == 0) { long long t = pclock(); ph[PH_RATES] += t - tc; }
     if (args.dbg_J) {   // diagnostics: in-kernel f and J at y0
-      eval_f(ks, x_off, DS, ph, ns);
+      eval_f(ks, x_off, DS, ph);
       for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = sm.savf[i];
       for (int q = tid; q < net.nstore; q += NT) ws.J[q] = 0.0;
       __syncthreads();
-      eval_jac(ks, x_off, ws.J, DS, ns);
+      eval_jac(ks, x_off, ws.J, DS);
       for (int q = tid; q < net.nstore; q += NT) args.dbg_J[(size_t)q * ncell + cell] = ws.J[q];
       __syncthreads();
       if (args.dbg_con != 0.0) {
-        const int fl = GLU ? factor_glu(ws, args.dbg_con, &s_flag, ph, net.glu.subst, ns) : factor<false>(ws, sm, lay, args.dbg_con, &s_flag, ph, ns);
+        const int fl = GLU ? factor_glu(ws, args.dbg_con, &s_flag, ph) : factor<false>(ws, sm, lay, args.dbg_con, &s_flag, ph);
         for (int i = tid; i < n; i += NT) sm.y[i] = sm.savf[i];
         __syncthreads();
-        if (GLU) solve_glu(ws, ph, net.glu.subst, ns); else solve(ws, sm, false, 1.0, ns);
+        if (GLU) { if (ell1) solve_glu<1>(ws, ph); else solve_glu<2>(ws, ph); } else solve(ws, sm, false, 1.0);
         for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = fl ? nan("") : sm.y[i];
         __syncthreads();
       }
@@ -1483,14 +1318,6 @@ integrate_kernel(const BatchArgs args) {
     double t = t_start, t_step = args.dt_first[cell], tout = t + t_step;
     int NERR = 0, nerr_c = 0, quality = 0, ISTATE = 1, n_record_real = 1;
     long long aNST = 0, aNFE = 0, aNJE = 0, aNLU = 0, nrestart = 0;
-    // block-solve mode (RACG_SUBST bits: 1 = L blocks, 2 = U blocks of the tail, 8 = U blocks of the
-    // S rows by substitution instead of explicit inverses).  On a few very stiff, hot cells one
-    // mode or the other lets round-off in the linear solves defeat the corrector (thousands of
-    // convergence failures where the reference algorithm has none): such a cell is integrated
-    // again from its initial state with the tail's U blocks treated the other way.
-    const bool second_try = redo_mask >= 0;
-    const int subst = second_try ? redo_mask : net.glu.subst;
-    redo_mask = -1;
     Lsodes s;
     s.NST = s.NFE = s.NJE = s.NLU = s.NQU = 0; s.HU = 0.0; s.INIT = 0; s.IMXER = 0;
     s.n_solve = s.n_cfail = s.n_efail = 0; s.wiped = 0; s.pw = 0.0;
@@ -1520,7 +1347,10 @@ integrate_kernel(const BatchArgs args) {
         const double TOUT = tout;
         int dl;   // driver label
         enum { D_BLOCKC, D200, D245, D250, D270, D_STEP, D_AFTER, D_INTERP, D345, D400, D420, D560, D580, D_RET };
+        if (ISTATE == 1) s.INIT = 0;
         if (ISTATE == 1 && TOUT == t) { dl = D_RET; }
+        else if (ISTATE != 1 && s.INIT == 0) { ISTATE = -3; dl = D_RET; }   // "ISTATE > 1 but DLSODES not initialized" (src/opkdmain.f:3087, error 603):
+                                                                              // the first step after a restart failed, then chem_evol_solve asks for ISTATE = 3
         else if (ISTATE == 2) dl = D200;
         else {
           // Block B
@@ -1537,7 +1367,7 @@ integrate_kernel(const BatchArgs args) {
             case D_BLOCKC: {
               s.TN = t; s.NST = 0; s.H = 1.0;
               FORE { yh[e][0] = sm.y[i]; yh[e][2] = 0.0; yh[e][3] = 0.0; yh[e][4] = 0.0; yh[e][5] = 0.0; }
-              { long long ta = clock64(); eval_f(ks, x_off, DS, ph, ns); if (tid == 0) ph[PH_F] += clock64() - ta; }
+              { long long ta = pclock(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += pclock() - ta; }
               FORE yh[e][1] = sm.savf[i];
               s.NFE = 1;
               bool bad = false;
@@ -1618,7 +1448,7 @@ integrate_kernel(const BatchArgs args) {
             }
             case D_STEP: {
               // ======================= DSTODE =======================
-              long long tv = clock64();
+              long long tv = pclock();
               int pc;
               double DCON, DDN, DEL = 0.0, DELP = 0.0, DSM = 0.0, DUP, R_, RH = 0.0, RHDN, RHSM, RHUP = 0.0, TOLD;
               int IREDO = 0, IRET = 0, M = 0, NCF = 0, NEWQ = 0;
@@ -1683,9 +1513,9 @@ integrate_kernel(const BatchArgs args) {
                   case L220: {
                     M = 0;
                     FORE sm.y[i] = yh[e][0];
-                    if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); eval_f(ks, x_off, DS, ph, ns); if (tid == 0) ph[PH_F] += clock64() - ta; }
-                    tv = clock64();
+                    if (tid == 0) ph[PH_VEC] += pclock() - tv;
+                    { long long ta = pclock(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += pclock() - ta; }
+                    tv = pclock();
                     s.NFE = s.NFE + 1;
                     if (s.IPUP <= 0) { pc = L250; break; }
                     // ---------------- DPRJS (src/opkda1.f:1735-1838) ----------------
@@ -1715,11 +1545,11 @@ integrate_kernel(const BatchArgs args) {
                       }
                       if (JOK == 0) {
                         s.JCUR = 1; s.NJE = s.NJE + 1; s.NSLJ = s.NST; s.IPLOST = 0; s.CONMIN = fabs(CON);
-                        if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                        long long ta = clock64();
-                        eval_jac(ks, x_off, ws.J, DS, ns);
-                        if (tid == 0) ph[PH_JAC] += clock64() - ta;
-                        tv = clock64();
+                        if (tid == 0) ph[PH_VEC] += pclock() - tv;
+                        long long ta = pclock();
+                        eval_jac(ks, x_off, ws.J, DS);
+                        if (tid == 0) ph[PH_JAC] += pclock() - ta;
+                        tv = pclock();
                         s.wiped = 0;
                       }
                       s.NLU = s.NLU + 1;
@@ -1727,9 +1557,9 @@ integrate_kernel(const BatchArgs args) {
                       if (s.wiped) {
                         flag = (s.pw == 0.0 || isnan(s.pw)) ? 1 : 0;
                       } else {
-                        if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                        flag = GLU ? factor_glu(ws, CON, &s_flag, ph, subst, ns) : factor<false>(ws, sm, lay, CON, &s_flag, ph, ns);
-                        tv = clock64();
+                        if (tid == 0) ph[PH_VEC] += pclock() - tv;
+                        flag = GLU ? factor_glu(ws, CON, &s_flag, ph) : factor<false>(ws, sm, lay, CON, &s_flag, ph);
+                        tv = pclock();
                       }
                       s.CON0 = CON;
                       s.IERPJ = flag ? 1 : 0;
@@ -1745,12 +1575,12 @@ integrate_kernel(const BatchArgs args) {
                     __syncthreads();
                     FORE sm.y[i] = s.H * sm.savf[i] - (yh[e][1] + acor[e]);
                     __syncthreads();
-                    if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); if (s.wiped) { for (int i = tid; i < n; i += NT) sm.y[i] = sm.y[i] / s.pw; __syncthreads(); }
-                      else if (GLU) solve_glu(ws, ph, subst, ns);
-                      else solve(ws, sm, false, s.pw, ns);
-                      if (tid == 0) ph[PH_SOLVE] += clock64() - ta; }
-                    tv = clock64();
+                    if (tid == 0) ph[PH_VEC] += pclock() - tv;
+                    { long long ta = pclock(); if (s.wiped) { for (int i = tid; i < n; i += NT) sm.y[i] = sm.y[i] / s.pw; __syncthreads(); }
+                      else if (GLU) { if (ell1) solve_glu<1>(ws, ph); else solve_glu<2>(ws, ph); }
+                      else solve(ws, sm, false, s.pw);
+                      if (tid == 0) ph[PH_SOLVE] += pclock() - ta; }
+                    tv = pclock();
                     s.n_solve++;
                     DEL = wrms_reg([&](int, int i) { return sm.y[i]; });
                     FORE { acor[e] = acor[e] + sm.y[i]; sm.y[i] = yh[e][0] + s.EL1 * acor[e]; }
@@ -1761,9 +1591,9 @@ integrate_kernel(const BatchArgs args) {
                     if (M == s.MAXCOR) { pc = L410; break; }
                     if (M >= 2 && DEL > 2.0 * DELP) { pc = L410; break; }
                     DELP = DEL;
-                    if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); __syncthreads(); eval_f(ks, x_off, DS, ph, ns); if (tid == 0) ph[PH_F] += clock64() - ta; }
-                    tv = clock64();
+                    if (tid == 0) ph[PH_VEC] += pclock() - tv;
+                    { long long ta = pclock(); __syncthreads(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += pclock() - ta; }
+                    tv = pclock();
                     s.NFE = s.NFE + 1;
                     pc = L270;
                     break;
@@ -1878,9 +1708,9 @@ integrate_kernel(const BatchArgs args) {
                     s.H = s.H * RH;
                     __syncthreads();
                     FORE sm.y[i] = yh[e][0];
-                    if (tid == 0) ph[PH_VEC] += clock64() - tv;
-                    { long long ta = clock64(); __syncthreads(); eval_f(ks, x_off, DS, ph, ns); if (tid == 0) ph[PH_F] += clock64() - ta; }
-                    tv = clock64();
+                    if (tid == 0) ph[PH_VEC] += pclock() - tv;
+                    { long long ta = pclock(); __syncthreads(); eval_f(ks, x_off, DS, ph); if (tid == 0) ph[PH_F] += pclock() - ta; }
+                    tv = pclock();
                     s.NFE = s.NFE + 1;
                     FORE yh[e][1] = s.H * sm.savf[i];
                     s.IPUP = 1; s.IALTH = 5;
@@ -1903,7 +1733,7 @@ integrate_kernel(const BatchArgs args) {
                 }
               }
               s.HOLD = s.H; s.JSTART = 1;
-              if (tid == 0) ph[PH_VEC] += clock64() - tv;
+              if (tid == 0) ph[PH_VEC] += pclock() - tv;
               // ===================== end DSTODE =====================
               if (s.KFLAG == 0) { dl = D_AFTER; break; }
               if (s.KFLAG == -1) { ISTATE = -4; dl = D560; break; }
@@ -1986,7 +1816,6 @@ integrate_kernel(const BatchArgs args) {
       __syncthreads();
       record_out(irec);
       n_record_real = irec;
-      if (GLU && !second_try && !(net.glu.subst & 16) && s.n_cfail > 4000) { redo_mask = subst ^ 2; break; }
       if (budget) {
         const double time_thisstep = net.rt_coef[0] * (double)(aNFE + s.NFE) + net.rt_coef[1] * (double)(aNJE + s.NJE) +
                                      net.rt_coef[2] * (double)(aNLU + s.NLU) + net.rt_coef[3] * (double)s.n_solve +
@@ -2022,18 +1851,7 @@ integrate_kernel(const BatchArgs args) {
       t_step = t_step * ratio;
       tout = t + t_step;
     }
-    // an abnormal end of the first attempt (unphysical abundances, illegal input, DLSODES -7)
-    // earns the same second chance as the corrector-failure count
-    if (GLU && !second_try && !(net.glu.subst & 16) && redo_mask < 0 && (quality & (256 | 512 | 1024))) redo_mask = subst ^ 2;
-    if (redo_mask >= 0) {
-      cNST = aNST + s.NST; cNFE = aNFE + s.NFE; cNJE = aNJE + s.NJE; cNLU = aNLU + s.NLU;
-      cSOL = s.n_solve; cCF = s.n_cfail; cEF = s.n_efail;
-      continue;
-    }
-    // the counters report all the work done for the cell, an abandoned first attempt included
-    aNST += s.NST + cNST; aNFE += s.NFE + cNFE; aNJE += s.NJE + cNJE; aNLU += s.NLU + cNLU;
-    s.n_solve += (int)cSOL; s.n_cfail += (int)cCF; s.n_efail += (int)cEF;
-    cNST = cNFE = cNJE = cNLU = cSOL = cCF = cEF = 0;
+    aNST += s.NST; aNFE += s.NFE; aNJE += s.NJE; aNLU += s.NLU;
     // records after an early exit are filled with the last state (src/chemistry.f90:570-575)
     if (args.touts || args.record) for (int r2 = n_record_real + 1; r2 <= args.sp.nrec_max; ++r2) record_out(r2);
     if (NERR > (int)(0.1f * (float)n_record_formula)) quality += 1;
@@ -2130,10 +1948,9 @@ size_t integrate_smem_bytes(DevNet& net) {
     const size_t xs = (size_t)net.ubE.npartial + (size_t)net.lcE.npartial + 64;
     if (xs > x_f) x_f = xs;
     if (2 * n > x_f) x_f = 2 * n;
-    if ((size_t)(NW / 2) * 33 * 32 > x_f) x_f = (size_t)(NW / 2) * 33 * 32;
     x_f = (x_f + 1) & ~(size_t)1;
     const size_t big = (227 * 1024 - 1024) / 8;
-    const size_t doff = (2 * n + net.nh + 32 + 2 * NW + 1) & ~(size_t)1;   // int4 descriptors (16-byte aligned)
+    const size_t doff = (3 * n + 32 + 2 * NW + 1) & ~(size_t)1;   // int4 descriptors (16-byte aligned)
     const size_t voff = doff + 2 * (size_t)net.glu.ndesc;
     const size_t xg = (size_t)(net.o_tl - net.o_ub);
     const size_t sinv = x_f, tab = sinv + (size_t)net.ss.nblkS * 33 * 32;
@@ -2153,17 +1970,24 @@ size_t integrate_ws_doubles(const DevNet& net) {
   return (w + 15) & ~(size_t)15;
 }
 
-#undef c_net
-// one-time upload of a handle's descriptor into its constant-memory slot (racg_network_create)
-cudaError_t upload_net_slot(int slot, const DevNet& net) {
-  if (slot < 0 || slot >= RACG_MAX_NETS) return cudaErrorInvalidValue;
-  return cudaMemcpyToSymbol(c_nets, &net, sizeof(DevNet), (size_t)slot * sizeof(DevNet), cudaMemcpyHostToDevice);
-}
+// per-device launch serialisation of the single constant-memory descriptor (see c_net)
+struct DevSerial { std::mutex mu; cudaEvent_t done = nullptr; unsigned long long owner = 0; };
+static DevSerial g_serial[64];
 
-cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nblocks, size_t smem,
-                             cudaStream_t stream) {
-  if (net.nt > 16 * MAXTL || (net.nt & 15)) return cudaErrorInvalidValue;
+cudaError_t launch_integrate(const DevNet& net, unsigned long long net_id, int device, const BatchArgs& args,
+                             int nblocks, size_t smem, cudaStream_t stream) {
+  if (net.nt > 16 * MAXTL || (net.nt & 15) || device < 0 || device >= 64) return cudaErrorInvalidValue;
+  DevSerial& S = g_serial[device];
+  std::lock_guard<std::mutex> lk(S.mu);
   cudaError_t e;
+  if (!S.done) { e = cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+  else { e = cudaStreamWaitEvent(stream, S.done, 0); if (e != cudaSuccess) return e; }
+  if (S.owner != net_id) {
+    // pageable source: the copy is staged before the call returns, the write is in stream order
+    e = cudaMemcpyToSymbolAsync(c_net, &net, sizeof(DevNet), 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    S.owner = net_id;
+  }
   const Layout L = make_layout(net);
   const bool all = L.glu != 0;
   auto go = [&](auto kern) -> cudaError_t {
@@ -2172,11 +1996,20 @@ cudaError_t launch_integrate(const DevNet& net, const BatchArgs& args, int nbloc
     kern<<<nblocks, NT, smem, stream>>>(args);
     return cudaSuccess;
   };
+  // elements per thread of the state vectors: n <= EPT * NT (build_host_net limits N to 1000)
+#if RACG_NT == 512
+  if (net.n <= NT) e = all ? go(integrate_kernel<1, true>) : go(integrate_kernel<1, false>);
+  else if (net.n <= 2 * NT) e = all ? go(integrate_kernel<2, true>) : go(integrate_kernel<2, false>);
+#else
   if (net.n <= 2 * NT) e = all ? go(integrate_kernel<2, true>) : go(integrate_kernel<2, false>);
   else if (net.n <= 3 * NT) e = all ? go(integrate_kernel<3, true>) : go(integrate_kernel<3, false>);
-  else e = go(integrate_kernel<4, false>);
+  else if (net.n <= 4 * NT) e = go(integrate_kernel<4, false>);
+#endif
+  else return cudaErrorInvalidValue;
   if (e != cudaSuccess) return e;
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return cudaEventRecord(S.done, stream);
 }
 
 }  // namespace racg
