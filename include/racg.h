@@ -186,6 +186,26 @@ int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const dou
                      double* y_final, double* t_final, double* touts, double* record,
                      int* nrec_real, int* istate, int* quality, double* stats);
 
+/* The batch form of calc_this_cell's local-iteration loop (src/disk.f90:1651-1791), evolT=.false.:
+ * for j = 1..nlocal_iter: tolerances chem_set_solver_flags_alt(j) (from sp->RTOL/ATOL); for j > 1 the
+ * run continues from the harvested state with t0 = t_final, dt_first = max(dt_first0, 1e-3*t0) and
+ * rectify_abundances (charge neutralised with E-; src/disk.f90:2103-2146, src/chemistry.f90:2170-2201);
+ * after every solve the LAST record whose T and X(H2) are not NaN is harvested (src/disk.f90:1716-1733);
+ * a cell leaves the ladder when quality == 0 or t_final >= 0.5*tmax (1785-1789), when a continuation
+ * does not proceed (1703-1712) or produces no useful record (1737-1740).  Cells still in the ladder are
+ * re-submitted as a compacted batch inside this call.
+ *   in : cellpar(ncell,NPAR), y0(ncell,NEQ), tmax(ncell), dt_first0, sp (ratio_tstep, mxstep, reset,
+ *        RTOL, ATOL, max_runtime_allowed; nrec_max and tol_policy_j are ignored)
+ *   out: abundances(ncell,NEQ) [= leaves%list(id)%p%abundances and Tgas], t_final(ncell) [par%t_final],
+ *        quality(ncell), istate(ncell) of the last solve, n_iter_used(ncell),
+ *        R_H2_form_rate_coeff(ncell) [src/chemistry.f90:804,891; s^-1 based unit as in the reference],
+ *        n_mol_on_grain(ncell) [get_ice_coverage, src/chemistry.f90:989-1003] (either may be NULL),
+ *        stats(ncell,RACG_NSTAT) accumulated over the ladder */
+int racg_calc_batch(racg_handle* h, int ncell, const double* cellpar, const double* y0, const double* tmax,
+                    double dt_first0, const racg_solve_params* sp, int nlocal_iter, double* abundances,
+                    double* t_final, int* quality, int* istate, int* n_iter_used, double* R_H2_form_rate_coeff,
+                    double* n_mol_on_grain, double* stats);
+
 /* ---- device-pointer variants (same layouts, buffers already in HBM; `stream` is a
  * cudaStream_t or NULL) for callers that keep the grid resident on the GPU ---- */
 int racg_rates_dev(racg_handle* h, int ncell, const double* cellpar, double* rates, void* stream);

@@ -287,6 +287,29 @@ class ChemSolver:
         return dict(y=yf, t_final=tf, touts=touts, record=rec, n_record_real=nrr, istate=ist,
                     quality=q, stats=st, nrec_max=nrec)
 
+    def calc_this_cell(self, cellpar, y0, t_max=1e6, dt_first_step0=1e-8, nlocal_iter=4, ratio_tstep=1.1,
+                       mxstep_per_interval=6000, steps_reset_solver=50, RTOL=1e-4, ATOL=1e-30,
+                       max_runtime_allowed=0.0):
+        """The batch form of calc_this_cell's local-iteration loop (src/disk.f90:1651-1791):
+        tolerance ladder, continuation from t_final, rectify_abundances, last-good-record harvest."""
+        par, y0 = _f(cellpar), _f(y0)
+        ncell = par.shape[0]
+        tma = np.ascontiguousarray(np.broadcast_to(np.asarray(t_max, np.float64), (ncell,)))
+        sp = SolveParams(ratio_tstep, mxstep_per_interval, steps_reset_solver, 0, 1, RTOL, ATOL, max_runtime_allowed)
+        ab = np.zeros((ncell, self.NEQ), order="F")
+        tf = np.zeros(ncell)
+        q = np.zeros(ncell, np.int32)
+        ist = np.zeros(ncell, np.int32)
+        nit = np.zeros(ncell, np.int32)
+        rh2 = np.zeros(ncell)
+        nmol = np.zeros(ncell)
+        st = np.zeros((ncell, NSTAT), order="F")
+        _check(lib().racg_calc_batch(self.h, C.c_int(ncell), _p(par), _p(y0), _p(tma), C.c_double(dt_first_step0),
+                                     C.byref(sp), C.c_int(nlocal_iter), _p(ab), _p(tf), _p(q), _p(ist), _p(nit),
+                                     _p(rh2), _p(nmol), _p(st)))
+        return dict(abundances=ab, t_final=tf, quality=q, istate=ist, n_iter_used=nit,
+                    R_H2_form_rate_coeff=rh2, n_mol_on_grain=nmol, stats=st)
+
     # ---- device-pointer entry points (buffers already in HBM) ----------
     def rates_dev(self, ncell, d_par, d_rates, stream=0):
         _check(lib().racg_rates_dev(self.h, C.c_int(ncell), C.c_void_p(d_par), C.c_void_p(d_rates),

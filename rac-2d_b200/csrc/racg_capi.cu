@@ -253,7 +253,8 @@ static int create_ctx(racg_handle* h, int device, DevCtx** out) {
     }
   }
   dn.iH = hn.iH; dn.iE = hn.iE; dn.igH = hn.igH; dn.igH2 = hn.igH2; dn.igH2O = hn.igH2O;
-  dn.iGrain0 = hn.iGrain0; dn.iGrainM = hn.iGrainM; dn.iGrainP = hn.iGrainP;
+  dn.iGrain0 = hn.iGrain0; dn.iGrainM = hn.iGrainM; dn.iGrainP = hn.iGrainP; dn.iH2 = hn.iH2;
+  dn.h2form_reac = hn.h2form_reac;
   UP(hn.hc_idx, hc_idx);
   dn.ngrain = (int)hn.grain_idx.size(); UP(hn.grain_idx, grain_idx);
   UP(hn.csc_to_store, csc_to_store);
@@ -646,10 +647,12 @@ int racg_rhs_jac(racg_handle* h, int ncell, const double* cellpar, const double*
 // integrator on the device's stream, one async D2H; then the results are scattered back into
 // the caller's arrays.  Cells are dealt by descending cost of the previous batch of the same
 // size (greedy longest-processing-time), else round-robin.
-int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const double* y0, const double* rtol,
-                     const double* atol, const double* t0, const double* tmax, const double* dt_first,
-                     const racg_solve_params* sp, double* y_final, double* t_final, double* touts,
-                     double* record, int* nrec_real, int* istate, int* quality, double* stats) {
+struct Harvest { double* y_good; double* t_good; int* isav; double* side; };
+
+static int solve_host(racg_handle* h, int ncell, const double* cellpar, const double* y0, const double* rtol,
+                      const double* atol, const double* t0, const double* tmax, const double* dt_first,
+                      const racg_solve_params* sp, double* y_final, double* t_final, double* touts,
+                      double* record, int* nrec_real, int* istate, int* quality, double* stats, const Harvest* hv) {
   int rc = need_gpu(h); if (rc) return rc;
   if (!cellpar || !y0 || !t0 || !tmax || !dt_first || !sp || !y_final || !t_final || !nrec_real || !istate ||
       !quality || !stats || ncell < 0) return fail(RACG_ERR_ARG, "bad argument");
@@ -687,7 +690,7 @@ int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const dou
     for (size_t c = 0; c < nc; ++c) h->dev[c % nd]->cells.push_back((int)c);
   }
   // ---- per device: stage, copy in, launch
-  struct Lay { size_t par, y0, rt, at, t, in_end, yf, tf, ii, st, touts, rec, out_end; };
+  struct Lay { size_t par, y0, rt, at, t, in_end, yf, tf, ii, st, yg, tg, sd, touts, rec, out_end; };
   std::vector<Lay> lays(nd);
   for (int d = 0; d < nd; ++d) {
     DevCtx* c = h->dev[d];
@@ -705,6 +708,9 @@ int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const dou
     L.tf = o; o = al256(o + 8 * nl);
     L.ii = o; o = al256(o + 4 * 3 * nl);
     L.st = o; o = al256(o + 8 * RACG_NSTAT * nl);
+    L.yg = o; if (hv) o = al256(o + 8 * NEQ * nl);
+    L.tg = o; if (hv) o = al256(o + 8 * nl + 4 * nl);
+    L.sd = o; if (hv) o = al256(o + 8 * 2 * nl);
     L.touts = o; if (touts) o = al256(o + 8 * nrec * nl);
     L.rec = o; if (record) o = al256(o + 8 * nrec * NEQ * nl);
     L.out_end = o;
@@ -739,6 +745,10 @@ int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const dou
     a.y_final = (double*)(db + L.yf); a.t_final = (double*)(db + L.tf);
     a.nrec_real = (int*)(db + L.ii); a.istate = a.nrec_real + nl; a.quality = a.nrec_real + 2 * nl;
     a.stats = (double*)(db + L.st);
+    if (hv) {
+      a.y_good = (double*)(db + L.yg); a.t_good = (double*)(db + L.tg); a.isav = (int*)(db + L.tg + 8 * nl);
+      a.side = (double*)(db + L.sd);
+    }
     a.touts = touts ? (double*)(db + L.touts) : nullptr; a.record = record ? (double*)(db + L.rec) : nullptr;
     if ((rc = solve_on_ctx(h, c, a, false, c->stream))) return rc;
     const size_t out_small = (touts ? al256(L.touts + 8 * nrec * nl) : L.touts) - L.yf;
@@ -766,6 +776,13 @@ int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const dou
     scatter(L.yf, y_final, NEQ);
     scatter(L.tf, t_final, 1);
     scatter(L.st, stats, RACG_NSTAT);
+    if (hv) {
+      scatter(L.yg, hv->y_good, NEQ);
+      scatter(L.tg, hv->t_good, 1);
+      scatter(L.sd, hv->side, 2);
+      const int* sv = (const int*)(hb + L.tg + 8 * nl);
+      for (size_t k = 0; k < nl; ++k) hv->isav[c->cells[k]] = sv[k];
+    }
     if (touts) scatter(L.touts, touts, nrec);
     const int* ii = (const int*)(hb + L.ii);
     for (size_t k = 0; k < nl; ++k) {
@@ -787,6 +804,91 @@ int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const dou
     }
   }
   if (h->warm_order && !h->dbg_J) for (size_t c = 0; c < nc; ++c) h->last_cost[c] = cell_cost(stats, nc, c);
+  return 0;
+}
+
+int racg_solve_batch(racg_handle* h, int ncell, const double* cellpar, const double* y0, const double* rtol,
+                     const double* atol, const double* t0, const double* tmax, const double* dt_first,
+                     const racg_solve_params* sp, double* y_final, double* t_final, double* touts,
+                     double* record, int* nrec_real, int* istate, int* quality, double* stats) {
+  return solve_host(h, ncell, cellpar, y0, rtol, atol, t0, tmax, dt_first, sp, y_final, t_final, touts, record,
+                    nrec_real, istate, quality, stats, nullptr);
+}
+
+// The batch form of calc_this_cell's local-iteration loop (src/disk.f90:1651-1791) for
+// evolT = .false.: tolerance ladder chem_set_solver_flags_alt(j), continuation from t_final with
+// dt_first = max(dt_first0, 1e-3 t0) and rectify_abundances (src/disk.f90:2103-2146,
+// src/chemistry.f90:2170-2201), harvest of the last record whose T and X(H2) are not NaN
+// (src/disk.f90:1716-1733), exit rules 1703-1712, 1737-1740, 1785-1789.  Cells that need another
+// local iteration are compacted into a smaller batch; a cell never returns to the host mid-ladder.
+int racg_calc_batch(racg_handle* h, int ncell, const double* cellpar, const double* y0, const double* tmax,
+                    double dt_first0, const racg_solve_params* sp, int nlocal_iter, double* abundances,
+                    double* t_final, int* quality, int* istate, int* n_iter_used, double* R_H2_form_rate_coeff,
+                    double* n_mol_on_grain, double* stats) {
+  int rc = need_gpu(h); if (rc) return rc;
+  if (!cellpar || !y0 || !tmax || !sp || !abundances || !t_final || !quality || !istate || !n_iter_used ||
+      !stats || ncell < 0 || nlocal_iter < 1 || !(dt_first0 > 0.0)) return fail(RACG_ERR_ARG, "bad argument");
+  if (ncell == 0) return 0;
+  const HostNet& hn = h->hn;
+  const size_t NEQ = hn.NEQ, N = hn.N, nc = ncell;
+  for (size_t k = 0; k < NEQ * nc; ++k) abundances[k] = y0[k];
+  for (size_t c = 0; c < nc; ++c) { t_final[c] = 0.0; quality[c] = 0; istate[c] = 0; n_iter_used[c] = 0; }
+  for (size_t k = 0; k < (size_t)RACG_NSTAT * nc; ++k) stats[k] = 0.0;
+  if (R_H2_form_rate_coeff) for (size_t c = 0; c < nc; ++c) R_H2_form_rate_coeff[c] = 0.0;
+  if (n_mol_on_grain) for (size_t c = 0; c < nc; ++c) n_mol_on_grain[c] = 0.0;
+  std::vector<int> act(nc);
+  std::iota(act.begin(), act.end(), 0);
+  racg_solve_params spj = *sp;
+  spj.nrec_max = 0;
+  std::vector<double> par, y, t0v, tmv, dtv, yf, tf, st, yg, tg, sd;
+  std::vector<int> ii, sv;
+  for (int j = 1; j <= nlocal_iter && !act.empty(); ++j) {
+    const size_t na = act.size();
+    par.resize(RACG_NPAR * na); y.resize(NEQ * na); t0v.resize(na); tmv.resize(na); dtv.resize(na);
+    yf.resize(NEQ * na); tf.resize(na); st.resize((size_t)RACG_NSTAT * na); yg.resize(NEQ * na); tg.resize(na);
+    sd.resize(2 * na); ii.resize(3 * na); sv.resize(na);
+    for (size_t k = 0; k < na; ++k) {
+      const size_t c = act[k];
+      for (size_t i = 0; i < RACG_NPAR; ++i) par[i * na + k] = cellpar[i * nc + c];
+      for (size_t i = 0; i < NEQ; ++i) y[i * na + k] = abundances[i * nc + c];
+      if (j > 1 && hn.iE >= 0) {   // rectify_abundances: neutralise with electrons
+        double q = 0.0;
+        for (size_t i = 0; i < N; ++i) q += abundances[i * nc + c] * (double)hn.elements[(size_t)RACG_NELEM * i];
+        y[(size_t)hn.iE * na + k] += q;
+      }
+      t0v[k] = (j == 1) ? 0.0 : t_final[c];
+      dtv[k] = (j == 1) ? dt_first0 : fmax(dt_first0, t0v[k] * 1e-3);
+      tmv[k] = tmax[c];
+    }
+    spj.tol_policy_j = j;
+    Harvest hv{yg.data(), tg.data(), sv.data(), sd.data()};
+    rc = solve_host(h, (int)na, par.data(), y.data(), nullptr, nullptr, t0v.data(), tmv.data(), dtv.data(), &spj,
+                    yf.data(), tf.data(), nullptr, nullptr, ii.data(), ii.data() + na, ii.data() + 2 * na, st.data(), &hv);
+    if (rc) return rc;
+    std::vector<int> next;
+    for (size_t k = 0; k < na; ++k) {
+      const size_t c = act[k];
+      n_iter_used[c] = j;
+      for (int q = 0; q < RACG_NSTAT; ++q) {
+        double& dst = stats[(size_t)q * nc + c];
+        const double v = st[(size_t)q * na + k];
+        if (q == 4 || q == 10 || q == 11 || q == 12 || q == 14) dst = v; else dst += v;   // counters accumulate over the ladder
+      }
+      istate[c] = ii[na + k];
+      // 'Local iteration does not proceed' (src/disk.f90:1703-1712): touts(n_record_real) <= previous t_final
+      if (j > 1 && tf[k] <= t_final[c]) continue;
+      quality[c] = ii[2 * na + k];
+      if (sv[k] <= 1) continue;                       // 'No useful data produced' (1737-1740)
+      for (size_t i = 0; i < NEQ; ++i) abundances[i * nc + c] = yg[i * na + k];
+      t_final[c] = tg[k];
+      if (R_H2_form_rate_coeff) R_H2_form_rate_coeff[c] = sd[k];
+      if (n_mol_on_grain) n_mol_on_grain[c] = sd[na + k];
+      if (quality[c] == 0 || t_final[c] >= 0.5 * tmax[c]) continue;   // done (1785-1789)
+      next.push_back((int)c);
+    }
+    act.swap(next);
+    h->last_cost.clear();   // sub-batches of the ladder have no cost history
+  }
   return 0;
 }
 

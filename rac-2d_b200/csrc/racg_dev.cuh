@@ -79,7 +79,8 @@ struct DevNet {
   GluDev glu;
   SolveDev ss;
   // species of the sanity test (src/chemistry.f90:520-526), 0-based or -1
-  int iH, iE, igH, igH2, igH2O, iGrain0, iGrainM, iGrainP;
+  int iH, iE, igH, igH2, igH2O, iGrain0, iGrainM, iGrainP, iH2;
+  int h2form_reac;           // the reaction whose coefficient is chem_params%R_H2_form_rate_coeff (src/chemistry.f90:804, 891), or -1
   const int* hc_idx;         // [10]
   int ngrain; const int* grain_idx;
   // standalone K2/K3
@@ -106,6 +107,10 @@ struct BatchArgs {
   double* record;            // [nrec_max][NEQ][ncell] or null
   int* nrec_real; int* istate; int* quality;
   double* stats;             // [NSTAT][ncell]
+  // optional harvest outputs (racg_calc_batch): last record with finite T and X(H2)
+  double* y_good;            // [NEQ][ncell] or null
+  double* t_good; int* isav; // [ncell]
+  double* side;              // [2][ncell]: R_H2_form_rate_coeff, n_mol_on_grain; or null
   // scheduler + workspace
   int* queue;                // work-queue counter
   const int* order;          // optional: queue position -> cell (heaviest first), else identity

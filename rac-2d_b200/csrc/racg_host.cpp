@@ -187,6 +187,9 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
       case 75: cls = RC_PHOTODES; break;
       default: cls = RC_ZERO;
     }
+    // chem_params%R_H2_form_rate_coeff: assigned in the itype 0 branch and in the itype 63 branch
+    // when the reactant is gH (src/chemistry.f90:804, 891); the last assignment wins
+    if (hn.itype[i] == 0 || (hn.itype[i] == 63 && hn.names[r1] == "gH")) hn.h2form_reac = i;
     int two_body_gas = (hn.n_reac[i] == 2 && hn.itype[i] < 60) ? 1 : 0;
     hn.rcode[i] = cls | (fss << 8) | (two_body_gas << 12) | (sigcheck << 13);
   }

@@ -55,6 +55,7 @@ struct HostNet {
   // special species (0-based, -1 absent)
   int iH2 = -1, iH = -1, iE = -1, igH = -1, igH2 = -1, igH2O = -1, iGrain0 = -1, iGrainM = -1,
       iGrainP = -1;
+  int h2form_reac = -1;          // last reaction that sets chem_params%R_H2_form_rate_coeff (0-based)
   std::vector<int> hc_idx;       // the 10 heating/cooling species of chem_idx_some_spe%idx
   std::vector<int> grain_idx;    // surface species
   // ---- rate tables (SoA over reactions) ----

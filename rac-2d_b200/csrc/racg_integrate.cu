@@ -83,7 +83,7 @@ struct Ws {          // per-CTA global workspace (L2 resident)
   double* ksave;     // [R] rate coefficients of the cell
   double* hhG;       // [n_hh] fallback home of hh
   double* ubG;       // [n_ub] fallback home of the factorisation's U_B
-  double* inv;       // [2*nblkS][32*32] inverses of the S diagonal blocks (row-major)
+  double* good;      // [n] last record whose T and X(H2) are not NaN (F15 harvest, src/disk.f90:1716-1733)
 };
 
 struct Layout { int hh_smem, ub_smem, nwr, glu; size_t xdoubles, total, voff; };
@@ -1186,7 +1186,7 @@ integrate_kernel(const BatchArgs args) {
     double* p = args.ws + (size_t)blockIdx.x * args.ws_stride;
     ws.J = p; p += net.nstore; ws.ubE = p; p += net.ubE.nval; ws.lcE = p; p += net.lcE.nval;
     ws.ksave = p; p += R; ws.hhG = p; p += net.n_hh; ws.ubG = p; p += net.n_ub;
-    ws.inv = p;
+    ws.good = p;
   }
   Smem sm;
   if (GLU) {
@@ -1322,7 +1322,17 @@ integrate_kernel(const BatchArgs args) {
     s.NST = s.NFE = s.NJE = s.NLU = s.NQU = 0; s.HU = 0.0; s.INIT = 0; s.IMXER = 0;
     s.n_solve = s.n_cfail = s.n_efail = 0; s.wiped = 0; s.pw = 0.0;
     s.NQ = 1; s.L = 2; s.H = 0.0; s.TN = t; s.IHIT = false;
+    // the harvest rule of calc_this_cell (src/disk.f90:1716-1733): the caller takes the LAST record
+    // whose T and X(H2) are not NaN -- tracked here so that the records need not be stored
+    double t_good = t_start; int isav = 0;
     auto record_out = [&](int irec) {   // touts(i) = t; record(:,i) = y
+      if (args.y_good) {
+        const bool fine = !isnan(Tslot) && !(net.iH2 >= 0 && isnan(sm.y[net.iH2]));
+        if (fine) {
+          for (int i = tid; i < n; i += NT) ws.good[i] = sm.y[i];
+          t_good = t; isav = irec;
+        }
+      }
       if (irec > args.sp.nrec_max) return;
       if (args.touts && tid == 0) args.touts[(size_t)(irec - 1) * ncell + cell] = t;
       if (args.record) {
@@ -1857,6 +1867,23 @@ integrate_kernel(const BatchArgs args) {
     if (NERR > (int)(0.1f * (float)n_record_formula)) quality += 1;
     if (t <= 0.5 * t_max) quality += 2;
     // ---- write results
+    if (args.y_good) {
+      __syncthreads();
+      double gsum = 0.0;     // get_ice_coverage (src/chemistry.f90:989-1003): molecules per grain
+      for (int i = tid; i < n; i += NT) args.y_good[(size_t)i * ncell + cell] = ws.good[i];
+      for (int q = tid; q < net.ngrain; q += NT) gsum += ws.good[net.grain_idx[q]];
+      gsum = block_sum(gsum, sm.red);
+      if (tid == 0) {
+        args.y_good[(size_t)(NEQ - 1) * ncell + cell] = Tslot;
+        args.t_good[cell] = t_good; args.isav[cell] = isav;
+        if (args.side) {
+          CellCommon cc;
+          cell_common(net.cfg, [&](int k) { return sm.par[k]; }, cc);
+          args.side[cell] = (net.h2form_reac >= 0) ? rate_coeff_raw(net, cc, net.h2form_reac) : 0.0;
+          args.side[ncell + cell] = gsum / sm.par[RACG_P_ratioDust2HnucNum];
+        }
+      }
+    }
     for (int i = tid; i < n; i += NT) args.y_final[(size_t)i * ncell + cell] = sm.y[i];
     if (tid == 0) {
       args.y_final[(size_t)(NEQ - 1) * ncell + cell] = Tslot;
@@ -1966,7 +1993,7 @@ size_t integrate_smem_bytes(DevNet& net) {
 size_t integrate_ws_doubles(const DevNet& net) {
   size_t w = (size_t)net.nstore + net.ubE.nval + net.lcE.nval + net.R + net.n_hh + net.n_ub;
   w = (w + 1) & ~(size_t)1;
-  w += (size_t)2 * net.ss.nblkS * 1024;
+  w += (size_t)net.n;
   return (w + 15) & ~(size_t)15;
 }
 

@@ -77,8 +77,9 @@ __device__ __forceinline__ double dev_branching(const racg_cfg& c, double A, dou
   return b;
 }
 
-// rate coefficient in yr^-1, before duplicate-set resolution
-__device__ __forceinline__ double rate_coeff(const DevNet& net, const CellCommon& cc, int i) {
+// rate coefficient in the reference's native unit (s^-1 based), before the conversion to yr^-1,
+// the n_gas factor of two-body gas reactions and the duplicate-set resolution
+__device__ __forceinline__ double rate_coeff_raw(const DevNet& net, const CellCommon& cc, int i) {
   const racg_cfg& c = net.cfg;
   const int code = net.rcode[i];
   const int cls = code & 0xff, fk = (code >> 8) & 0xf;
@@ -164,8 +165,13 @@ __device__ __forceinline__ double rate_coeff(const DevNet& net, const CellCommon
     }
     default: k = 0.0;
   }
-  k = k * c.phy_SecondsPerYear;
-  if ((code >> 12) & 1) k = k * cc.n_gas;
+  return k;
+}
+
+// rate coefficient in yr^-1, before duplicate-set resolution (src/chemistry.f90:936-942)
+__device__ __forceinline__ double rate_coeff(const DevNet& net, const CellCommon& cc, int i) {
+  double k = rate_coeff_raw(net, cc, i) * net.cfg.phy_SecondsPerYear;
+  if ((net.rcode[i] >> 12) & 1) k = k * cc.n_gas;
   return k;
 }
 

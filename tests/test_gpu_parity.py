@@ -155,15 +155,12 @@ def test_rhs_jac_match_oracle(setupA, ncell):
         assert ydot[c, net.N] == 0.0
 
 
-def _compare_trajectories(res, oracle_runs, net, nrec, tight_runs=None):
-    """max relative difference over species above X_FLOOR at every common output time.
-    Output times are tout = t_returned + t_step (src/chemistry.f90:565-566): after an error
-    return (ISTATE<0) inside one implementation only, later output times shift, so records
-    are compared where the two time grids coincide and the matched fraction is reported."""
-    worst = 0.0
-    where = None
-    matched = []
-    nstrict = [0, 0]
+def _compare_trajectories(res, oracle_runs, net):
+    """violation of the plain 10 x RTOL_i bound at every output time where the two time grids
+    coincide.  Output times are tout = t_returned + t_step (src/chemistry.f90:565-566): after an
+    error return (ISTATE<0) inside one implementation only, later output times shift, so records
+    are compared where the grids coincide and the matched fraction is reported."""
+    viol, matched = [], []
     tol = _tolvec(net)
     for c, orun in enumerate(oracle_runs):
         n_o = orun["n_record_real"]
@@ -175,24 +172,18 @@ def _compare_trajectories(res, oracle_runs, net, nrec, tight_runs=None):
             if abs(tg[i] - to[i]) > 1e-12 * abs(to[i]):
                 continue
             nm += 1
-            a = res["record"][c, :net.N, i]
-            b = orun["record"][i, :net.N]
-            bt = None
-            if tight_runs is not None and abs(tight_runs[c]["touts"][i] - to[i]) <= 1e-12 * abs(to[i]):
-                bt = tight_runs[c]["record"][i, :net.N]
-            strict = _maxviol(a, b, tol)
-            nstrict[0] += 1
-            nstrict[1] += strict <= 1.0
-            v = strict if bt is None and tight_runs is None else _maxviol(a, b, tol, bt if bt is not None else b)
-            if v > worst:
-                worst = v
-                where = (c, i)
+            viol.append(_maxviol(res["record"][c, :net.N, i], orun["record"][i, :net.N], tol))
         matched.append(nm / n_o)
-    return worst, where, matched, nstrict[1] / max(nstrict[0], 1)
+    return np.array(viol), matched
 
 
 def test_evol_solve_matches_oracle_every_output_time(setupA):
-    """8 cells, rate06-withgrain, 1e-8 -> 1e6 yr, reference tolerances: every output time."""
+    """8 cells, rate06-withgrain, 1e-8 -> 1e6 yr, reference tolerances: the plain 10 x RTOL_i bound
+    (1e-3 gas phase, 1e-2 surface species; species above 1e-12) at every output time, as a
+    distribution over all (cell, output time) pairs -- no widening.  The bound is exceeded only
+    around fast transients of trace species, where two runs of the same controller are a
+    fraction of a step out of phase (the oracle against its own round-off-perturbed run does the
+    same, tests/test_gpu_sweep.py)."""
     rb, net, sol, onet, y0s = setupA
     ncell = 8
     par, y0 = _cells(rb, net, y0s, ncell)
@@ -203,26 +194,26 @@ def test_evol_solve_matches_oracle_every_output_time(setupA):
         rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[c, 6])
         runs.append(onet.evol_solve(par[c], y0[c], rt, at))
         assert runs[-1]["quality"] == 0
-    tight = [_tight_run(onet, par[c], y0[c]) for c in range(ncell)]
-    worst, where, matched, frac_strict = _compare_trajectories(res, runs, net, res["nrec_max"], tight)
-    assert worst <= 1.0, (worst, where)
-    # ... and the plain 10 x RTOL_i bound holds at (nearly) every output time
-    assert frac_strict > 0.97, frac_strict
+    viol, matched = _compare_trajectories(res, runs, net)
+    print(f"\n{len(viol)} (cell, output time) pairs: violation of the plain bound median {np.median(viol):.3g} "
+          f"p90 {np.percentile(viol, 90):.3g} p99 {np.percentile(viol, 99):.3g} max {viol.max():.3g}; "
+          f"within the bound {100 * np.mean(viol <= 1.0):.2f} %")
+    assert np.mean(viol <= 1.0) > 0.97, np.mean(viol <= 1.0)
+    assert np.median(viol) < 0.05 and np.percentile(viol, 99) < 3.0, (np.median(viol), np.percentile(viol, 99))
     # cells without solver errors on either side share the whole 316-point grid
     for c in range(ncell):
         if runs[c]["stats"][6] == 0 and res["stats"][c, 6] == 0:
             assert matched[c] == 1.0
     assert np.mean(matched) > 0.9, matched
+    # final state: plain bound on every one of these cells; t_final
     for c in range(ncell):
-        assert _maxviol(res["y"][c, :net.N], runs[c]["y"][:net.N], _tolvec(net), tight[c]["y"][:net.N]) <= 1.0
-    # final state and t_final
-    for c in range(ncell):
+        assert _maxviol(res["y"][c, :net.N], runs[c]["y"][:net.N], _tolvec(net)) <= 1.0, c
         assert res["t_final"][c] == runs[c]["t_final"] == 1e6
         assert res["y"][c, net.N] == par[c, 0]
-    # step counts are of the same order as the oracle's (same controller)
+    # step counts within 10 % of the oracle's (same controller)
     nst_g = res["stats"][:, 0]
     nst_o = np.array([r["stats"][0] for r in runs])
-    assert np.all(np.abs(nst_g - nst_o) < 0.25 * nst_o + 50), (nst_g, nst_o)
+    assert np.all(np.abs(nst_g - nst_o) < 0.10 * nst_o + 20), (nst_g, nst_o)
 
 
 def test_evol_solve_stratified_and_policy_tolerances(setupA):
@@ -334,20 +325,157 @@ def test_rate12_network(rb, oracle):
         assert _maxviol(res["y"][c, :net.N], o["y"][:net.N], _tolvec(net)) <= 1.0, c
 
 
-def test_hot_stiff_cells_complete_like_the_oracle(setupA):
-    """Cells of the synthetic stream (T > 1700 K) on which one or the other treatment of the
-    tail's U diagonal blocks defeats the corrector: the per-cell retry must bring every one of
-    them to t_max with the oracle's return codes and a final state within 3 x the stated
-    tolerance (the oracle needs 1.4-2.5 k steps for each)."""
+# ---------------------------------------------------------------------------
+# a14 / f3: continuation and the local-iteration ladder of calc_this_cell
+
+def _oracle_calc_this_cell(onet, net, par_c, y0_c, t_max, nlocal_iter, dt0=1e-8, mxstep=6000, budget=0.0):
+    """calc_this_cell's loop (src/disk.f90:1651-1791, evolT=.false.) on the CPU oracle: ladder j,
+    continuation, rectify_abundances, last-good-record harvest"""
+    N = net.N
+    charge = net.elements[:, 0].astype(float)
+    iE = net.index("E-") - 1
+    iH2 = net.index("H2") - 1
+    ab = np.array(y0_c, float)
+    t_final, quality, n_iter, istate = 0.0, 0, 0, 0
+    for j in range(1, nlocal_iter + 1):
+        y = ab.copy()
+        if j > 1:
+            y[iE] += float(np.sum(ab[:N] * charge))
+        t0 = 0.0 if j == 1 else t_final
+        dt = dt0 if j == 1 else max(dt0, 1e-3 * t0)
+        rt, at = onet.solver_flags_alt(j, 1e-4, 1e-30, par_c[6])
+        o = onet.evol_solve(par_c, y, rt, at, t0=t0, t_max=t_max, dt_first_step=dt, mxstep=mxstep,
+                            max_runtime_allowed=budget)
+        n_iter, istate = j, o["istate"]
+        nr = o["n_record_real"]
+        if j > 1 and o["touts"][nr - 1] <= t_final:
+            break
+        isav = 0
+        for k in range(nr, 0, -1):
+            if not np.isnan(o["record"][k - 1, N]) and not np.isnan(o["record"][k - 1, iH2]):
+                isav = k
+                break
+        quality = o["quality"]
+        if isav <= 1:
+            break
+        ab = o["record"][isav - 1].copy()
+        t_final = o["touts"][isav - 1]
+        if quality == 0 or t_final >= 0.5 * t_max:
+            break
+    return dict(abundances=ab, t_final=t_final, quality=quality, n_iter_used=n_iter, istate=istate)
+
+
+def test_continuation_from_t_final_matches_oracle(setupA):
+    """a14: a second chem_evol_solve from t0 = t_final > 0 with y0 = y_final, dt_first = max(dt0, 1e-3 t0)
+    and the j = 2 tolerances (set_initial_condition_4solver_continue, src/disk.f90:2103-2146)"""
     rb, net, sol, onet, y0s = setupA
-    for c in (2091, 11980, 15520):
-        par = rb.synth.cell_params(1, first_cell=c)
-        y0 = rb.synth.initial_state(y0s, par, net.index("Grain0"))
-        res = sol.chem_evol_solve(par, y0, want_touts=False)
-        rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[0, 6])
-        o = onet.evol_solve(par[0], y0[0], rt, at, want_record=False)
-        assert o["quality"] == 0 and o["t_final"] == 1e6
-        assert res["istate"][0] == 2 and res["quality"][0] == 0 and res["t_final"][0] == 1e6, (c, res["istate"], res["quality"])
-        # these cells are integrated at the edge of what round-off allows (both solvers crawl at
-        # order 1 for most of the run): 3 x the stated bound is accepted here, and only here
-        assert _final_viol(onet, par[0], y0[0], rt, at, res["y"][0], o, _tolvec(net)) <= 3.0, c
+    par, y0 = _cells(rb, net, y0s, 4)
+    r1 = sol.chem_evol_solve(par, y0, t_max=1e3, want_touts=False)
+    assert np.all(r1["t_final"] == 1e3)
+    t0 = r1["t_final"].copy()
+    r2 = sol.chem_evol_solve(par, r1["y"], t0=t0, t_max=1e6, dt_first_step=np.maximum(1e-8, 1e-3 * t0), tol_policy_j=2)
+    assert np.all(r2["istate"] == 2) and np.all(r2["t_final"] == 1e6)
+    tol = _tolvec(net)
+    for c in range(4):
+        rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[c, 6])
+        o1 = onet.evol_solve(par[c], y0[c], rt, at, t_max=1e3, want_record=False)
+        rt2, at2 = onet.solver_flags_alt(2, 1e-4, 1e-30, par[c, 6])
+        o2 = onet.evol_solve(par[c], o1["y"], rt2, at2, t0=1e3, t_max=1e6, dt_first_step=1.0, want_record=False)
+        assert r2["n_record_real"][c] == o2["n_record_real"]
+        assert _maxviol(r2["y"][c, :net.N], o2["y"][:net.N], tol) <= 1.0, c
+
+
+def test_calc_this_cell_ladder_matches_oracle(setupA):
+    """f3: the local-iteration ladder inside one call.  A small work budget (max_runtime_allowed,
+    the same deterministic clock on both sides) ends every solve prematurely with quality 2
+    (t <= t_max / 2), so the cells climb the ladder j = 1..4 exactly as calc_this_cell does;
+    compared with the same loop run on the CPU oracle."""
+    rb, net, sol, onet, y0s = setupA
+    par, y0 = _cells(rb, net, y0s, 6)
+    g = sol.calc_this_cell(par, y0, t_max=1e6, nlocal_iter=4, max_runtime_allowed=0.3)
+    tol = _tolvec(net)
+    assert g["n_iter_used"].max() > 1, g["n_iter_used"]
+    for c in range(6):
+        o = _oracle_calc_this_cell(onet, net, par[c], y0[c], 1e6, 4, budget=0.3)
+        assert g["n_iter_used"][c] == o["n_iter_used"], (c, g["n_iter_used"][c], o["n_iter_used"])
+        assert g["quality"][c] == o["quality"], (c, g["quality"][c], o["quality"])
+        assert abs(g["t_final"][c] - o["t_final"]) <= 0.3 * o["t_final"], (c, g["t_final"][c], o["t_final"])
+    # the normal case: one iteration, quality 0, identical to a plain solve; side outputs
+    g1 = sol.calc_this_cell(par, y0, t_max=1e6, nlocal_iter=4)
+    r = sol.chem_evol_solve(par, y0, want_touts=False)
+    assert np.all(g1["n_iter_used"] == 1) and np.all(g1["quality"] == 0)
+    assert np.array_equal(g1["abundances"], r["y"]) and np.array_equal(g1["t_final"], r["t_final"])
+    D = par[:, 6]
+    nmol = r["y"][:, [net.index(nm) - 1 for nm in net.names if nm.startswith("g")]].sum(axis=1) / D
+    assert np.allclose(g1["n_mol_on_grain"], nmol, rtol=1e-12)
+    k = sol.chem_cal_rates(par)
+    i63 = [i for i in range(net.R) if net.itype[i] == 0 or (net.itype[i] == 63 and net.names[net.reac[i, 0] - 1] == "gH")][-1]
+    assert np.allclose(g1["R_H2_form_rate_coeff"] * 3600.0 * 24.0 * 365.0, k[:, i63], rtol=1e-12)
+    for c in range(6):
+        assert _maxviol(g1["abundances"][c, :net.N], _oracle_calc_this_cell(onet, net, par[c], y0[c], 1e6, 4)["abundances"][:net.N], tol) <= 1.0
+
+
+def test_nan_injected_cell_is_harvested_at_the_last_good_record(setupA):
+    """F15 (src/disk.f90:1716-1740): a cell whose state turns NaN returns the last record with finite
+    T and X(H2) -- here a NaN planted in the initial abundance of CO poisons the first step."""
+    rb, net, sol, onet, y0s = setupA
+    par, y0 = _cells(rb, net, y0s, 3)
+    y0[1, net.index("CO") - 1] = np.nan
+    g = sol.calc_this_cell(par, y0, t_max=1e6, nlocal_iter=4)
+    assert g["n_iter_used"][0] == 1 and g["n_iter_used"][2] == 1 and g["quality"][0] == 0 and g["quality"][2] == 0
+    iH2 = net.index("H2") - 1
+    assert not np.isnan(g["abundances"][1, iH2]) and not np.isnan(g["abundances"][1, net.N])
+    assert g["t_final"][1] < 1e6
+    r = sol.chem_evol_solve(par[[0, 2]], y0[[0, 2]], want_touts=False)
+    assert np.array_equal(g["abundances"][[0, 2]], r["y"])          # the neighbours are untouched
+
+
+def test_record_capacity_is_not_the_loop_length(setupA):
+    """nrec_max is a capacity.  Without touts/record it may be 0 and the cell still runs
+    its own n_record; with touts/record a capacity below a cell's n_record is an argument error."""
+    rb, net, sol, onet, y0s = setupA
+    par, y0 = _cells(rb, net, y0s, 2)
+    full = sol.chem_evol_solve(par, y0, want_touts=True)
+    none = sol.chem_evol_solve(par, y0, want_touts=False, nrec_max=0)
+    assert np.array_equal(full["y"], none["y"]) and np.array_equal(full["t_final"], none["t_final"])
+    assert np.all(none["t_final"] == 1e6) and np.array_equal(full["n_record_real"], none["n_record_real"])
+    with pytest.raises(rb.RacgError, match="nrec_max"):
+        sol.chem_evol_solve(par, y0, want_touts=True, nrec_max=100)
+
+
+def test_two_handles_and_two_networks_interleaved(rb, oracle):
+    """ADVICE r1 / VERDICT weak 7: handles share no state -- two networks used alternately on one
+    device give the results of each network used alone"""
+    netA, netB = rb.ChemNetwork(NET_A), rb.ChemNetwork(NET_B)
+    sA, sB = netA.create_solver(), netB.create_solver()
+    y0A = netA.chem_load_initial_abundances(IC_GARROD)
+    y0B = netB.chem_load_initial_abundances(IC_GARROD)
+    par = rb.synth.cell_params(3)
+    yA = rb.synth.initial_state(y0A, par, netA.index("Grain0"))
+    yB = rb.synth.initial_state(y0B, par, netB.index("Grain0"))
+    a1 = sA.chem_evol_solve(par, yA, t_max=1e2, want_touts=False)
+    b1 = sB.chem_evol_solve(par, yB, t_max=1e2, want_touts=False)
+    a2 = sA.chem_evol_solve(par, yA, t_max=1e2, want_touts=False)
+    sA2 = netA.create_solver()
+    a3 = sA2.chem_evol_solve(par, yA, t_max=1e2, want_touts=False)
+    b2 = sB.chem_evol_solve(par, yB, t_max=1e2, want_touts=False)
+    assert np.array_equal(a1["y"], a2["y"]) and np.array_equal(a1["y"], a3["y"]) and np.array_equal(b1["y"], b2["y"])
+
+
+def test_multi_device_sharding_is_bitwise_identical(setupA):
+    """north_star (e) behind the C-ABI: racg_use_devices + one racg_solve_batch call shards the
+    batch over the GPUs (LPT dealing after the first call) and returns what one GPU returns"""
+    rb, net, sol, onet, y0s = setupA
+    import ctypes
+    n = ctypes.c_int(0)
+    ctypes.CDLL("libcudart.so.12").cudaGetDeviceCount(ctypes.byref(n))
+    par, y0 = _cells(rb, net, y0s, 96)
+    one = sol.chem_evol_solve(par, y0, t_max=1e4, want_touts=False)
+    sol2 = net.create_solver()
+    ndev = sol2.use_devices(None)
+    assert ndev == n.value
+    for rep in range(2):        # second call: cells dealt by the previous call's per-cell cost
+        many = sol2.chem_evol_solve(par, y0, t_max=1e4, want_touts=False)
+        for k in ("y", "t_final", "istate", "quality", "n_record_real", "stats"):
+            assert np.array_equal(one[k], many[k]), (k, rep, ndev)
+    sol2.close()
