@@ -4,6 +4,7 @@
 //   K3 jac_kernel       whole chem_ode_jac for every cell  (src/disk.f90:4746-4903)
 // Layout: every array is [item][cell] (Fortran a(ncell, item)), so that a warp
 // working on 32 consecutive cells of one item reads/writes 256 contiguous bytes.
+#include <cuda.h>            // CUtensorMap and its enums only; the encoder is fetched at run time
 #include <cuda_runtime.h>
 #include "racg_dev.cuh"
 #include "racg_rates.cuh"
@@ -114,6 +115,161 @@ rhs_kernel(const DevNet net, int ncell, const double* __restrict__ cellpar,
       if (ok) __stcs(ydot + (size_t)g.comb_row[m] * ncell + cell, sacc);
     }
     if (ok && q == 0) ydot[(size_t)(NEQ - 1) * ncell + cell] = 0.0;   // T slot, evolT = .false.
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2, streaming variant (the one launch_rhs uses whenever the network fits): HBM-bound design.
+//   * a CTA of 32 warps owns a tile of 16 consecutive cells: half-warp lane = cell, so every global
+//     access is a 128-byte row segment of the [item][cell] arrays and every shared-memory access is
+//     conflict-free; the two halves of a warp work on different reactions / species;
+//   * the tile's abundances y[n][16] stay in shared memory for the whole tile;
+//   * the rate coefficients -- 84 % of the bytes -- stream through a ring of NSTAGE shared-memory
+//     stages of RC reactions x 16 cells, each filled by TMA tile loads (cp.async.bulk.tensor.2d over
+//     a tensor map of rates[R][ncell], box 16 x 128, out-of-range rows/cells zero-filled,
+//     completion counted on an mbarrier) issued NSTAGE-1 chunks ahead of the arithmetic, across
+//     tile boundaries;
+//   * per chunk the fluxes are formed in place in the stage, then every half-warp adds them to the
+//     register accumulators of the <= SPW species it owns (HostNet::RhsChunks run lists: 16-bit
+//     indices of the chunk's rows, consumed terms then produced terms, each in reaction order);
+//     chunks are large (RC = 640) so that a run has several terms and its overhead is amortised;
+//   * ydot leaves as one coalesced row segment per species.
+// Persistent grid: one CTA per SM, tiles dealt round-robin.
+// (Tried first: 32-cell tiles with 128-reaction chunks -- 12 k runs of 1.5 terms per tile, 27 k
+// warp-instructions per cell, 5.2 ms for 75 776 cells; and one cp.async.bulk per row segment --
+// thousands of small copies per tile saturate the copy engine, 7.1 ms.)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int K2_TC = 16;          // cells per tile
+template <int SPW>
+__global__ void __launch_bounds__(1024, 1)
+rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant__ CUtensorMap rates_map, int ncell,
+                  int nstage, const double* __restrict__ cellpar, const double* __restrict__ y,
+                  double* __restrict__ ydot) {
+  extern __shared__ __align__(128) unsigned char smb[];
+  const int n = net.n, R = net.R, NEQ = net.NEQ, RC = rc.RC, nchunk = rc.nchunk;
+  const int STG = (RC + 1) * (K2_TC * 8);                // bytes per stage: RC rows + one zero row
+  double* const ys = (double*)smb;                       // [n][16]
+  unsigned char* const kb0 = smb + (size_t)n * (K2_TC * 8);
+  uint64_t* const bars = (uint64_t*)(kb0 + (size_t)nstage * STG);
+  const int tid = threadIdx.x, cl = tid & (K2_TC - 1), hw = tid >> 4;     // hw: half-warp 0..63
+  const int ntile = (ncell + K2_TC - 1) / K2_TC;
+  const int my_tiles = (ntile > (int)blockIdx.x) ? (ntile - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int G = my_tiles * nchunk;                       // chunks this CTA will consume
+  if (tid == 0) {
+    for (int s2 = 0; s2 < nstage; ++s2) mbar_init(bars + s2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < K2_TC) for (int s2 = 0; s2 < nstage; ++s2) ((double*)(kb0 + (size_t)s2 * STG))[RC * K2_TC + tid] = 0.0;
+  __syncthreads();
+  // producer (thread 0): chunk g of this CTA's stream -> stage g % nstage, RC/128 TMA boxes of 128 x 16
+  auto issue = [&](int g) {
+    const int ti = g / nchunk, c = g - ti * nchunk;
+    const int cell0 = ((int)blockIdx.x + ti * (int)gridDim.x) * K2_TC;
+    const int s2 = g % nstage;
+    mbar_expect_tx(bars + s2, (uint32_t)(RC * K2_TC * 8));    // whole boxes land, zero-filled where out of range
+    for (int b = 0; b < RC / 128; ++b)
+      tma_load_2d(kb0 + (size_t)s2 * STG + (size_t)b * 128 * (K2_TC * 8), &rates_map, cell0, c * RC + b * 128, bars + s2);
+  };
+  if (tid == 0) for (int g = 0; g < nstage - 1 && g < G; ++g) issue(g);
+  for (int ti = 0; ti < my_tiles; ++ti) {
+    const int cell0 = ((int)blockIdx.x + ti * (int)gridDim.x) * K2_TC;
+    const int cell = cell0 + cl;
+    const bool ok = cell < ncell;
+    for (int i = hw; i < n; i += 64) ys[i * K2_TC + cl] = ok ? __ldcs(y + (size_t)i * ncell + cell) : 0.0;
+    const double DS = ok ? cellpar[(size_t)RACG_P_ratioDust2HnucNum * ncell + cell] *
+                           cellpar[(size_t)RACG_P_SitesPerGrain * ncell + cell] : 1.0;
+    double acc[SPW];
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) acc[k] = 0.0;
+    __syncthreads();
+    for (int c = 0; c < nchunk; ++c) {
+      const int g = ti * nchunk + c, s2 = g % nstage;
+      if (tid == 0 && g + nstage - 1 < G) {
+        // the stage about to be refilled was last written through the generic proxy (fluxes)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(g + nstage - 1);
+      }
+      mbar_wait(bars + s2, (uint32_t)((g / nstage) & 1));
+      double* const kb = (double*)(kb0 + (size_t)s2 * STG) + cl;
+      // ---- fluxes in place (branches of chem_ode_f, src/disk.f90:4583-4643), one reaction per half-warp
+      for (int rl = hw; rl < RC; rl += 64) {
+        const int r = c * RC + rl;
+        double f = 0.0;
+        if (r < R) {
+          const uint32_t fwv = __ldg(net.fw + r);
+          const double k = kb[rl * K2_TC];
+          const int kind = (fwv >> 20) & 3;
+          const double y1 = ys[(fwv & 1023) * K2_TC + cl];
+          if (kind == FK_ONE) f = k * y1;
+          else if (kind == FK_TWO) {
+            const double y2 = ys[((fwv >> 10) & 1023) * K2_TC + cl];
+            f = k * y1 * y2;
+            if (y1 < 0.0 && y2 < 0.0) f = -f;
+          } else if (kind == FK_SAT) {
+            const double tmp1 = DS * net.sat_c[fwv >> 22];
+            if (tmp1 <= 0.0) f = k;
+            else { const double tmp = y1 / tmp1; f = (tmp <= 1e-4) ? k * tmp : k * (1.0 - exp(-tmp)); }
+          }
+        }
+        kb[rl * K2_TC] = f;
+      }
+      __syncthreads();
+      // ---- this half-warp's species: run lists of the chunk
+      {
+        const uint32_t* p = rc.stream + __ldg(rc.off + hw * nchunk + c);
+        const int nr = __ldg(rc.nrun + hw * nchunk + c);
+        uint32_t nxt = __ldg(p);     // the stream is read one word ahead
+        int q = 0;
+        // runs are listed by ascending slot: a static walk over the slots keeps acc[] in registers
+#pragma unroll
+        for (int kk = 0; kk < SPW; ++kk) {
+          if (q < nr && (int)(nxt & 31u) == kk) {
+            const int nm = (nxt >> 5) & 0x1fff, np = nxt >> 18;
+            nxt = __ldg(++p);
+            double a = acc[kk];
+            for (int i = 0; i < nm; ++i) {
+              const uint32_t e = nxt; nxt = __ldg(++p);
+              a -= kb[(e & 0xffffu) * K2_TC]; a -= kb[(e >> 16) * K2_TC];
+            }
+            for (int i = 0; i < np; ++i) {
+              const uint32_t e = nxt; nxt = __ldg(++p);
+              a += kb[(e & 0xffffu) * K2_TC]; a += kb[(e >> 16) * K2_TC];
+            }
+            acc[kk] = a;
+            ++q;
+          }
+        }
+      }
+      __syncthreads();     // every warp is done with the stage: it may be refilled
+    }
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < SPW; ++k) {
+        const int sp = (k < rc.spw) ? __ldg(rc.slot_species + hw * rc.spw + k) : -1;
+        if (sp >= 0) __stcs(ydot + (size_t)sp * ncell + cell, acc[k]);
+      }
+      if (hw == 0) ydot[(size_t)(NEQ - 1) * ncell + cell] = 0.0;   // T slot, evolT = .false.
+    }
   }
 }
 
@@ -314,8 +470,47 @@ constexpr int RHS_TC = 4;
 size_t rhs_smem_bytes(const DevNet& net) {
   return ((size_t)net.n + net.R + net.rhs.npartial + 1) * RHS_TC * sizeof(double);
 }
-cudaError_t launch_rhs(const DevNet& net, int ncell, const double* cellpar, const double* y, const double* rates,
-                       double* ydot, int nsm, cudaStream_t st) {
+// tensor map of rates[R][ncell] (f64, row pitch ncell*8) with a box of 16 cells x 128 reactions
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_rates_map(CUtensorMap* map, const double* rates, int R, int ncell) {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    else cudaGetLastError();
+  }
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)ncell, (cuuint64_t)R};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ncell * 8};
+  const cuuint32_t box[2] = {(cuuint32_t)K2_TC, 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)rates, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_rhs(const DevNet& net, const RhsChunkDev& rc, int ncell, const double* cellpar, const double* y,
+                       const double* rates, double* ydot, int nsm, cudaStream_t st) {
+  // streaming variant: the tensor map needs a 16-byte row pitch and base (even ncell); <= 8 species per half-warp
+  if (rc.spw <= 8 && rc.RC % 128 == 0 && rc.RC < 65535 && (ncell & 1) == 0 && ((size_t)rates & 15) == 0) {
+    const size_t stg = (size_t)(rc.RC + 1) * (K2_TC * 8), ybytes = (size_t)net.n * (K2_TC * 8);
+    int nstage = (int)((227 * 1024 - 256 - ybytes) / stg);
+    if (nstage > 3) nstage = 3;
+    CUtensorMap map;
+    if (nstage >= 2 && make_rates_map(&map, rates, net.R, ncell)) {
+      const size_t smem2 = ybytes + nstage * stg + 64;
+      cudaError_t e2 = cudaFuncSetAttribute(rhs_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e2 != cudaSuccess) return e2;
+      const int ntile = (ncell + K2_TC - 1) / K2_TC;
+      rhs_stream_kernel<8><<<ntile < nsm ? ntile : nsm, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
+      return cudaGetLastError();
+    }
+  }
   const size_t smem = rhs_smem_bytes(net);
   cudaError_t e = cudaFuncSetAttribute(rhs_kernel<RHS_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -29,8 +29,8 @@ cudaError_t launch_cost_order(int ncell, const double* stats, float* cost, int* 
 cudaError_t launch_cost(int ncell, const double* stats, float* cost, cudaStream_t st);
 // racg_batch.cu
 cudaError_t launch_rates(const DevNet& net, int ncell, const double* cellpar, double* rates, cudaStream_t st);
-cudaError_t launch_rhs(const DevNet& net, int ncell, const double* cellpar, const double* y, const double* rates,
-                       double* ydot, int nsm, cudaStream_t st);
+cudaError_t launch_rhs(const DevNet& net, const RhsChunkDev& rc, int ncell, const double* cellpar, const double* y,
+                       const double* rates, double* ydot, int nsm, cudaStream_t st);
 cudaError_t launch_jac(const DevNet& net, const JacColTables& jc, int ncell, const double* cellpar, const double* y,
                        const double* rates, double* pd, int nsm, cudaStream_t st);
 }  // namespace racg
@@ -51,6 +51,7 @@ struct DevCtx {
   unsigned long long net_id = 0;   // changes whenever dn changes
   DevNet dn;
   JacColTables jc;
+  RhsChunkDev rhsc;
   std::vector<void*> allocs;
   size_t smem_int = 0, ws_stride = 0;
   int nblocks = 0;
@@ -258,6 +259,15 @@ static int create_ctx(racg_handle* h, int device, DevCtx** out) {
   UP(hn.hc_idx, hc_idx);
   dn.ngrain = (int)hn.grain_idx.size(); UP(hn.grain_idx, grain_idx);
   UP(hn.csc_to_store, csc_to_store);
+  {
+    RhsChunkDev& r = c->rhsc;
+    const HostNet::RhsChunks& s = hn.rhsc;
+    r.RC = s.RC; r.nchunk = s.nchunk; r.spw = s.spw;
+    if ((rc = upload(c, s.slot_species, &r.slot_species))) return rc;
+    if ((rc = upload(c, s.off, &r.off))) return rc;
+    if ((rc = upload(c, s.nrun, &r.nrun))) return rc;
+    if ((rc = upload(c, s.stream, &r.stream))) return rc;
+  }
   {
     JacColTables& jc = c->jc;
     const HostNet::JacCols& s = hn.jc;
@@ -564,7 +574,7 @@ int racg_rhs_jac_dev(racg_handle* h, int ncell, const double* cellpar, const dou
   DeviceGuard guard;
   DevCtx* c = h->dev[0];
   CK(cudaSetDevice(c->device));
-  if (ydot) { CK(launch_rhs(c->dn, ncell, cellpar, y, rates, ydot, c->nsm, (cudaStream_t)stream)); h->launches += 1; }
+  if (ydot) { CK(launch_rhs(c->dn, c->rhsc, ncell, cellpar, y, rates, ydot, c->nsm, (cudaStream_t)stream)); h->launches += 1; }
   if (pd) { CK(launch_jac(c->dn, c->jc, ncell, cellpar, y, rates, pd, c->nsm, (cudaStream_t)stream)); h->launches += 1; }
   return 0;
 }

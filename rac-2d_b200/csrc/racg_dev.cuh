@@ -124,6 +124,12 @@ struct BatchArgs {
   double dbg_con;            // != 0: additionally factor P = I + dbg_con*J and return P^-1 f in y_final
 };
 
+// streaming K2 schedule (HostNet::RhsChunks)
+struct RhsChunkDev {
+  int RC, nchunk, spw;
+  const int* slot_species; const uint32_t* off; const int* nrun; const uint32_t* stream;
+};
+
 // stand-alone K3 column-group schedule (racg_batch.cu)
 struct JacColTables {
   int ngroups;

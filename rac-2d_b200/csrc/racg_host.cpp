@@ -233,6 +233,49 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   }
   hn.nsat = (int)hn.sat_c.size();
   build_gather(hn.rhs, sp_rows, 32);
+  // ---- streaming K2 schedule (HostNet::RhsChunks)
+  {
+    HostNet::RhsChunks& rc = hn.rhsc;
+    rc.RC = 640; rc.nchunk = (R + rc.RC - 1) / rc.RC; rc.nwarp = 64; rc.spw = (N + rc.nwarp - 1) / rc.nwarp;
+    // species -> (half-warp, slot): heaviest species first onto the least loaded owner with a free slot
+    std::vector<int> order(N);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sp_rows[a].size() > sp_rows[b].size(); });
+    std::vector<long> load(rc.nwarp, 0);
+    std::vector<int> used(rc.nwarp, 0);
+    rc.slot_species.assign((size_t)rc.nwarp * rc.spw, -1);
+    for (int sp : order) {
+      int best = -1;
+      for (int w = 0; w < rc.nwarp; ++w) if (used[w] < rc.spw && (best < 0 || load[w] < load[best])) best = w;
+      rc.slot_species[(size_t)best * rc.spw + used[best]++] = sp;
+      load[best] += (long)sp_rows[sp].size() + 4 * rc.nchunk;
+    }
+    rc.off.assign((size_t)rc.nwarp * rc.nchunk, 0); rc.nrun.assign((size_t)rc.nwarp * rc.nchunk, 0);
+    for (int w = 0; w < rc.nwarp; ++w)
+      for (int c = 0; c < rc.nchunk; ++c) {
+        rc.off[(size_t)w * rc.nchunk + c] = (uint32_t)rc.stream.size();
+        int nrun = 0;
+        for (int k = 0; k < rc.spw; ++k) {
+          const int sp = rc.slot_species[(size_t)w * rc.spw + k];
+          if (sp < 0) continue;
+          std::vector<uint16_t> em, ep;
+          for (auto& e : sp_rows[sp]) {
+            if (e.first / rc.RC != c) continue;
+            const int loc = e.first % rc.RC;
+            for (int m = 0; m < std::abs(e.second); ++m) (e.second < 0 ? em : ep).push_back((uint16_t)loc);
+          }
+          if (em.empty() && ep.empty()) continue;
+          if (em.size() % 2) em.push_back((uint16_t)rc.RC);
+          if (ep.size() % 2) ep.push_back((uint16_t)rc.RC);
+          rc.stream.push_back((uint32_t)k | ((uint32_t)(em.size() / 2) << 5) | ((uint32_t)(ep.size() / 2) << 18));
+          for (size_t q = 0; q < em.size(); q += 2) rc.stream.push_back((uint32_t)em[q] | ((uint32_t)em[q + 1] << 16));
+          for (size_t q = 0; q < ep.size(); q += 2) rc.stream.push_back((uint32_t)ep[q] | ((uint32_t)ep[q + 1] << 16));
+          ++nrun;
+        }
+        rc.nrun[(size_t)w * rc.nchunk + c] = nrun;
+      }
+    rc.stream.push_back(0u);   // the kernel reads one word ahead
+  }
 
   // ---- species-block pattern and fill-reducing ordering
   const int n = N;

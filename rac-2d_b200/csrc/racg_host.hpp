@@ -137,6 +137,21 @@ struct HostNet {
     std::vector<uint32_t> ext;     // S diagonal blocks: pos | tile offset << 16 (tile = b*33*32 + c*33 + r)
   } ss;
 
+  // ---- stand-alone K2, streaming variant (racg_batch.cu rhs_stream_kernel): reactions in chunks of
+  // RC rows whose rate coefficients arrive by TMA tile loads; the 64 half-warps of a CTA each own up
+  // to SPW species of a 16-cell tile (accumulators in registers).  Per (half-warp, chunk) a run list:
+  //   header word  = slot | n_minus_words << 5 | n_plus_words << 18
+  //   entry words  = 2 chunk-local reaction ids per word (padding id = RC: a zero row), first the
+  //                  consumed (-) then the produced (+) terms of the species inside the chunk, each in
+  //                  reaction order; a coefficient of magnitude m is m entries (as the reference's
+  //                  loop subtracts/adds the flux once per occurrence, src/disk.f90:4644-4650)
+  struct RhsChunks {
+    int RC = 0, nchunk = 0, nwarp = 64, spw = 0;   // nwarp = owners (half-warps)
+    std::vector<int> slot_species;      // [nwarp*spw] species id or -1
+    std::vector<uint32_t> off;          // [nwarp*nchunk] offset of the run list in stream
+    std::vector<int> nrun;              // [nwarp*nchunk]
+    std::vector<uint32_t> stream;
+  } rhsc;
   // ---- Jacobian gather into the storage index space, two passes (d/dy_r1, d/dy_r2) ----
   Gather jac[2];
   // map from the user's CSC slot (ia/ja) to the storage index or -1

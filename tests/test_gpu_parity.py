@@ -124,7 +124,7 @@ def _rel_to_scale(a, b, scale):
     return np.max(np.abs(a - b) / scale)
 
 
-@pytest.mark.parametrize("ncell", [70, 132])
+@pytest.mark.parametrize("ncell", [70, 71, 132])
 def test_rhs_jac_match_oracle(setupA, ncell):
     """ncell = 70: ragged against every tile size (K3 with one cell per lane); ncell = 132: a
     multiple of 4 (K3 with four cells per lane, jac_kernel4) but ragged against its 128-cell tile."""
