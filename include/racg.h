@@ -206,6 +206,18 @@ int racg_calc_batch(racg_handle* h, int ncell, const double* cellpar, const doub
                     double* t_final, int* quality, int* istate, int* n_iter_used, double* R_H2_form_rate_coeff,
                     double* n_mol_on_grain, double* stats);
 
+/* On-disk format of the reference's chemistry checkpoint (back_cells_chemical_data,
+ * src/data_dump.f90:88-162): 'chemical_data_iter_NNNN.bin' (iiter < 0: 'chemical_data.bin') in
+ * directory dir, a direct-access unformatted file whose record i holds abundances(1:nSpecies),
+ * col_den_toStar(1:ncd), col_den_toISM(1:ncd) of leaf i as native doubles (record length
+ * 8*(nSpecies+2*ncd) bytes, no record markers).  Written straight from the gathered batch arrays:
+ * abundances(ncell, >= nspecies) as returned by racg_calc_batch / racg_solve_batch,
+ * col_den_*(ncd, ncell) as the host keeps them.  Host only, no GPU needed. */
+int racg_write_chemical_data(const char* dir, int iiter, int ncell, int nspecies, const double* abundances,
+                             int ncd, const double* col_den_toStar, const double* col_den_toISM);
+int racg_read_chemical_data(const char* dir, int iiter, int ncell, int nspecies, double* abundances, int ncd,
+                            double* col_den_toStar, double* col_den_toISM);
+
 /* ---- device-pointer variants (same layouts, buffers already in HBM; `stream` is a
  * cudaStream_t or NULL) for callers that keep the grid resident on the GPU ---- */
 int racg_rates_dev(racg_handle* h, int ncell, const double* cellpar, double* rates, void* stream);

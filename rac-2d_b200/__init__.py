@@ -7,8 +7,8 @@ benchmark and ``__graft_entry__``.  There is no CPU fallback: every compute call
 through the CUDA library and raises if it is missing or no GPU is visible.
 """
 from .chem import (NPAR, NSTAT, ChemNetwork, ChemSolver, RacgError, SolveParams, build, default_cfg,
-                   lib, lib_path)
+                   lib, lib_path, read_chemical_data, write_chemical_data)
 from . import synth
 
 __all__ = ["NPAR", "NSTAT", "ChemNetwork", "ChemSolver", "RacgError", "SolveParams", "build",
-           "default_cfg", "lib", "lib_path", "synth"]
+           "default_cfg", "lib", "lib_path", "read_chemical_data", "write_chemical_data", "synth"]

@@ -157,6 +157,28 @@ class ChemNetwork:
             pass
 
 
+def write_chemical_data(dirname, iiter, abundances, col_den_toStar=None, col_den_toISM=None, nspecies=None):
+    """chemical_data_iter_NNNN.bin of the reference (src/data_dump.f90:88-162) from batch arrays:
+    abundances (ncell, >= nspecies), col_den_* (ncell, ncd)."""
+    ab = _f(abundances)
+    ncell = ab.shape[0]
+    ns = nspecies or ab.shape[1]
+    ncd = 0 if col_den_toStar is None else np.asarray(col_den_toStar).shape[1]
+    cs = np.ascontiguousarray(col_den_toStar, np.float64) if ncd else None
+    ci = np.ascontiguousarray(col_den_toISM, np.float64) if ncd else None
+    _check(lib().racg_write_chemical_data(dirname.encode(), C.c_int(iiter), C.c_int(ncell), C.c_int(ns), _p(ab),
+                                          C.c_int(ncd), _p(cs), _p(ci)))
+
+
+def read_chemical_data(dirname, iiter, ncell, nspecies, ncd):
+    ab = np.zeros((ncell, nspecies), order="F")
+    cs = np.zeros((ncell, ncd))
+    ci = np.zeros((ncell, ncd))
+    _check(lib().racg_read_chemical_data(dirname.encode(), C.c_int(iiter), C.c_int(ncell), C.c_int(nspecies), _p(ab),
+                                         C.c_int(ncd), _p(cs) if ncd else None, _p(ci) if ncd else None))
+    return ab, cs, ci
+
+
 class ChemSolver:
     """racg_handle: the GPU chemistry solver for one network."""
 

@@ -496,21 +496,31 @@ static bool make_rates_map(CUtensorMap* map, const double* rates, int R, int nce
 
 cudaError_t launch_rhs(const DevNet& net, const RhsChunkDev& rc, int ncell, const double* cellpar, const double* y,
                        const double* rates, double* ydot, int nsm, cudaStream_t st) {
-  // streaming variant: the tensor map needs a 16-byte row pitch and base (even ncell); <= 8 species per half-warp
-  if (rc.spw <= 8 && rc.RC % 128 == 0 && rc.RC < 65535 && (ncell & 1) == 0 && ((size_t)rates & 15) == 0) {
+  // streaming variant: the tensor map needs a 16-byte row pitch and base (even ncell); <= 16 species per half-warp
+  if (rc.spw <= 16 && rc.RC % 128 == 0 && rc.RC < 65535 && (ncell & 1) == 0 && ((size_t)rates & 15) == 0) {
     const size_t stg = (size_t)(rc.RC + 1) * (K2_TC * 8), ybytes = (size_t)net.n * (K2_TC * 8);
     int nstage = (int)((227 * 1024 - 256 - ybytes) / stg);
     if (nstage > 3) nstage = 3;
     CUtensorMap map;
     if (nstage >= 2 && make_rates_map(&map, rates, net.R, ncell)) {
       const size_t smem2 = ybytes + nstage * stg + 64;
-      cudaError_t e2 = cudaFuncSetAttribute(rhs_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      if (e2 != cudaSuccess) return e2;
       const int ntile = (ncell + K2_TC - 1) / K2_TC;
-      rhs_stream_kernel<8><<<ntile < nsm ? ntile : nsm, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
+      const int grid = ntile < nsm ? ntile : nsm;
+      cudaError_t e2;
+      if (rc.spw <= 8) {
+        e2 = cudaFuncSetAttribute(rhs_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) return e2;
+        rhs_stream_kernel<8><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
+      } else {
+        e2 = cudaFuncSetAttribute(rhs_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) return e2;
+        rhs_stream_kernel<16><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
+      }
       return cudaGetLastError();
     }
   }
+  // fallback (odd ncell, very large networks): 4-cell tiles with the whole flux tile in shared memory
+  if (rhs_smem_bytes(net) > 227 * 1024) return cudaErrorInvalidConfiguration;
   const size_t smem = rhs_smem_bytes(net);
   cudaError_t e = cudaFuncSetAttribute(rhs_kernel<RHS_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -957,6 +958,52 @@ int racg_selfcheck_damaged(const racg_handle* h, int mode) {
   else return fail(RACG_ERR_ARG, "unknown damage mode");
   std::string err;
   if (!selfcheck_schedules(copy, err)) return fail(RACG_ERR_NETWORK, "schedule self-check: " + err);
+  return 0;
+}
+
+// chemical_data_iter_NNNN.bin (back_cells_chemical_data, src/data_dump.f90:88-162): a direct-access
+// unformatted file, record i (fixed length, no record markers) = abundances(1:nSpecies),
+// col_den_toStar(1:ncd), col_den_toISM(1:ncd) of leaf i as native doubles; the file name follows
+// the reference ('chemical_data_iter_', I0.4, '.bin'; iiter < 0: 'chemical_data.bin').
+static std::string chemical_data_name(const char* dir, int iiter) {
+  char nm[64];
+  if (iiter >= 0) snprintf(nm, sizeof nm, "chemical_data_iter_%04d.bin", iiter); else snprintf(nm, sizeof nm, "chemical_data.bin");
+  std::string d = dir ? dir : ".";
+  if (!d.empty() && d.back() != '/') d += '/';
+  return d + nm;
+}
+
+int racg_write_chemical_data(const char* dir, int iiter, int ncell, int nspecies, const double* abundances,
+                             int ncd, const double* col_den_toStar, const double* col_den_toISM) {
+  if (!abundances || ncell < 0 || nspecies <= 0 || ncd < 0 || (ncd > 0 && (!col_den_toStar || !col_den_toISM)))
+    return fail(RACG_ERR_ARG, "bad argument");
+  const std::string fn = chemical_data_name(dir, iiter);
+  FILE* f = fopen(fn.c_str(), "wb");
+  if (!f) return fail(RACG_ERR_ARG, "cannot open " + fn);
+  std::vector<double> rec((size_t)nspecies + 2 * (size_t)ncd);
+  for (int c = 0; c < ncell; ++c) {
+    for (int i = 0; i < nspecies; ++i) rec[i] = abundances[(size_t)i * ncell + c];      // a(ncell, item)
+    for (int k = 0; k < ncd; ++k) { rec[nspecies + k] = col_den_toStar[(size_t)c * ncd + k]; rec[nspecies + ncd + k] = col_den_toISM[(size_t)c * ncd + k]; }
+    if (fwrite(rec.data(), sizeof(double), rec.size(), f) != rec.size()) { fclose(f); return fail(RACG_ERR_ARG, "write failed: " + fn); }
+  }
+  fclose(f);
+  return 0;
+}
+
+int racg_read_chemical_data(const char* dir, int iiter, int ncell, int nspecies, double* abundances, int ncd,
+                            double* col_den_toStar, double* col_den_toISM) {
+  if (!abundances || ncell < 0 || nspecies <= 0 || ncd < 0 || (ncd > 0 && (!col_den_toStar || !col_den_toISM)))
+    return fail(RACG_ERR_ARG, "bad argument");
+  const std::string fn = chemical_data_name(dir, iiter);
+  FILE* f = fopen(fn.c_str(), "rb");
+  if (!f) return fail(RACG_ERR_ARG, "cannot open " + fn);
+  std::vector<double> rec((size_t)nspecies + 2 * (size_t)ncd);
+  for (int c = 0; c < ncell; ++c) {
+    if (fread(rec.data(), sizeof(double), rec.size(), f) != rec.size()) { fclose(f); return fail(RACG_ERR_ARG, "short file: " + fn); }
+    for (int i = 0; i < nspecies; ++i) abundances[(size_t)i * ncell + c] = rec[i];
+    for (int k = 0; k < ncd; ++k) { col_den_toStar[(size_t)c * ncd + k] = rec[nspecies + k]; col_den_toISM[(size_t)c * ncd + k] = rec[nspecies + ncd + k]; }
+  }
+  fclose(f);
   return 0;
 }
 

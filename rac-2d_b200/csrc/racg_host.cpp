@@ -236,7 +236,11 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   // ---- streaming K2 schedule (HostNet::RhsChunks)
   {
     HostNet::RhsChunks& rc = hn.rhsc;
-    rc.RC = 640; rc.nchunk = (R + rc.RC - 1) / rc.RC; rc.nwarp = 64; rc.spw = (N + rc.nwarp - 1) / rc.nwarp;
+    // chunk size: two stages of (RC + 1) x 128 B beside the y tile of N x 128 B in 227 KB
+    rc.RC = ((int)((231000 - (long)N * 128) / 256) - 1) / 128 * 128;
+    if (rc.RC > 640) rc.RC = 640;
+    if (rc.RC < 128) rc.RC = 128;
+    rc.nchunk = (R + rc.RC - 1) / rc.RC; rc.nwarp = 64; rc.spw = (N + rc.nwarp - 1) / rc.nwarp;
     // species -> (half-warp, slot): heaviest species first onto the least loaded owner with a free slot
     std::vector<int> order(N);
     std::iota(order.begin(), order.end(), 0);

@@ -323,6 +323,23 @@ def test_rate12_network(rb, oracle):
         rt, at = onet.solver_flags_alt(1, 1e-4, 1e-30, par[c, 6])
         o = onet.evol_solve(par[c], y0[c], rt, at, want_record=False)
         assert _maxviol(res["y"][c, :net.N], o["y"][:net.N], _tolvec(net)) <= 1.0, c
+    # 48 cells of the stream (generic factorisation path: this network's factor does not fit in
+    # shared memory): return codes, step counts and the abundance distribution
+    import os
+    n = 48
+    par = rb.synth.cell_params(n, first_cell=100)
+    y0 = rb.synth.initial_state(y0s, par, net.index("Grain0"))
+    res = sol.chem_evol_solve(par, y0, want_touts=False, max_runtime_allowed=60.0)
+    o = onet.evol_solve_batch(par, y0, nthreads=os.cpu_count() or 1, max_runtime_allowed=60.0)
+    same = (res["istate"] == o["istate"]) & (res["quality"] == o["quality"]) & (res["t_final"] == o["t_final"])
+    assert same.sum() >= n - 2, (res["istate"], o["istate"], res["quality"], o["quality"])
+    nominal = same & (o["istate"] == 2) & (o["quality"] == 0) & (o["t_final"] == 1e6)
+    viol = np.array([_maxviol(res["y"][c, :net.N], o["y"][c, :net.N], _tolvec(net)) for c in np.where(nominal)[0]])
+    ratio = res["stats"][nominal, 0] / o["stats"][nominal, 0]
+    print(f"\nrate12, {int(nominal.sum())} nominal cells: plain-bound violation median {np.median(viol):.3g} "
+          f"p90 {np.percentile(viol, 90):.3g} max {viol.max():.3g}; NST ratio median {np.median(ratio):.3f}")
+    assert np.median(viol) < 0.2 and np.mean(viol <= 1.0) >= 0.85
+    assert abs(np.median(ratio) - 1.0) < 0.03 and np.mean(np.abs(ratio - 1.0) < 0.1) >= 0.9
 
 
 # ---------------------------------------------------------------------------

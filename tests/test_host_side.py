@@ -193,3 +193,24 @@ print("rank", rank, "ok")
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_chemical_data_file_has_the_reference_record_layout(rb, tmp_path):
+    """f4: chemical_data_iter_NNNN.bin (back_cells_chemical_data, src/data_dump.f90:88-162) is a
+    direct-access file of fixed-length records [abundances(nSpecies), col_den_toStar(ncd),
+    col_den_toISM(ncd)] in native doubles, one per leaf cell, no record markers."""
+    ncell, ns, ncd = 7, 467, 10
+    rng = np.random.default_rng(3)
+    ab = np.asfortranarray(rng.random((ncell, ns + 1)))      # batch layout incl. the T slot
+    cs, ci = rng.random((ncell, ncd)), rng.random((ncell, ncd))
+    rb.write_chemical_data(str(tmp_path), 12, ab, cs, ci, nspecies=ns)
+    fn = tmp_path / "chemical_data_iter_0012.bin"
+    raw = np.fromfile(fn, dtype=np.float64)
+    assert raw.size == ncell * (ns + 2 * ncd)                # record_len = 8 * (nSpecies + 2 ncd)
+    rec = raw.reshape(ncell, ns + 2 * ncd)
+    assert np.array_equal(rec[:, :ns], ab[:, :ns]) and np.array_equal(rec[:, ns:ns + ncd], cs)
+    assert np.array_equal(rec[:, ns + ncd:], ci)
+    ab2, cs2, ci2 = rb.read_chemical_data(str(tmp_path), 12, ncell, ns, ncd)
+    assert np.array_equal(ab2, ab[:, :ns]) and np.array_equal(cs2, cs) and np.array_equal(ci2, ci)
+    rb.write_chemical_data(str(tmp_path), -1, ab, nspecies=ns)
+    assert (tmp_path / "chemical_data.bin").stat().st_size == 8 * ncell * ns

@@ -1,7 +1,7 @@
 set -x
 mkdir -p gpurun_out/r2
-timeout 900 python bench.py > gpurun_out/r2/bench_1gpu.json 2> gpurun_out/r2/bench_1gpu.err; echo "bench rc=$?"
-tail -c 3000 gpurun_out/r2/bench_1gpu.json
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:integrate_kernel -c 1 --csv --log-file gpurun_out/r2/traffic_integrate.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2/ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
-cat gpurun_out/r2/traffic_integrate.csv | tail -5
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2/launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --ncell 2368 > gpurun_out/r2/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:jac_kernel4 -c 1 -o gpurun_out/r2/prof_k3 python tests/gpu_kernels_bw.py > gpurun_out/r2/ncu_k3.log 2>&1; echo "ncu rc=$?"
+timeout 1500 python bench.py --network rate12-withGrain --ncell 2000 --steps 2 --warmup 2 --cpu-cells 32 --kernel-ncell 37888 > gpurun_out/r2/bench_rate12.json 2> gpurun_out/r2/bench_rate12.err; echo "rate12 rc=$?"
+head -c 300 gpurun_out/r2/bench_rate12.json; tail -3 gpurun_out/r2/bench_rate12.err
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "rate12" --timeout 500 > gpurun_out/r2/pytest_rate12.log 2>&1; echo "pytest rc=$?"
+tail -8 gpurun_out/r2/pytest_rate12.log
