@@ -120,24 +120,25 @@ rhs_kernel(const DevNet net, int ncell, const double* __restrict__ cellpar,
 
 // ---------------------------------------------------------------------------
 // K2, streaming variant (the one launch_rhs uses whenever the network fits): HBM-bound design.
-//   * a CTA of 32 warps owns a tile of 16 consecutive cells: half-warp lane = cell, so every global
-//     access is a 128-byte row segment of the [item][cell] arrays and every shared-memory access is
-//     conflict-free; the two halves of a warp work on different reactions / species;
-//   * the tile's abundances y[n][16] stay in shared memory for the whole tile;
-//   * the rate coefficients -- 84 % of the bytes -- stream through a ring of NSTAGE shared-memory
-//     stages of RC reactions x 16 cells, each filled by TMA tile loads (cp.async.bulk.tensor.2d over
-//     a tensor map of rates[R][ncell], box 16 x 128, out-of-range rows/cells zero-filled,
-//     completion counted on an mbarrier) issued NSTAGE-1 chunks ahead of the arithmetic, across
-//     tile boundaries;
-//   * per chunk the fluxes are formed in place in the stage, then every half-warp adds them to the
-//     register accumulators of the <= SPW species it owns (HostNet::RhsChunks run lists: 16-bit
-//     indices of the chunk's rows, consumed terms then produced terms, each in reaction order);
-//     chunks are large (RC = 640) so that a run has several terms and its overhead is amortised;
+//   * a CTA of 32 warps owns a tile of 32 consecutive cells: lane = cell, so every global access is
+//     a 256-byte row segment of the [item][cell] arrays and every shared-memory access is
+//     conflict-free;
+//   * the rate coefficients -- 84 % of the bytes -- stream through a ring of 2 shared-memory stages
+//     of RC = 384 reactions x 32 cells, each filled by TMA tile loads (cp.async.bulk.tensor.2d over a
+//     tensor map of rates[R][ncell], box 32 x 128, out-of-range rows/cells zero-filled, completion
+//     counted on an mbarrier) issued one chunk ahead of the arithmetic, across tile boundaries;
+//   * per chunk the fluxes are formed in place in the stage from host-built lists sorted by flux
+//     kind (no branches in the loops; the abundances come straight from global memory: the tile's
+//     y rows are L1/L2 hits);
+//   * then every warp adds the fluxes to the register accumulators of the <= SPW species it owns
+//     (HostNet::RhsChunks run lists: byte offsets of the chunk's rows, 16-byte groups, consumed
+//     terms then produced terms, each in reaction order);
 //   * ydot leaves as one coalesced row segment per species.
 // Persistent grid: one CTA per SM, tiles dealt round-robin.
-// (Tried first: 32-cell tiles with 128-reaction chunks -- 12 k runs of 1.5 terms per tile, 27 k
-// warp-instructions per cell, 5.2 ms for 75 776 cells; and one cp.async.bulk per row segment --
-// thousands of small copies per tile saturate the copy engine, 7.1 ms.)
+// Measured on the way (75 776 cells): one cp.async.bulk per 256-byte row segment 7.1 ms (thousands
+// of small copies per tile saturate the copy engine); 32-cell tiles with 128-reaction chunks and y
+// in shared memory 5.2 ms (12 k runs of 1.5 terms per tile: 27 k warp-instructions per cell);
+// 16-cell tiles with 640-reaction chunks 3.25 ms (half-warps diverge, 21 k per cell).
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
@@ -159,49 +160,47 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
                :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int K2_TC = 16;          // cells per tile
+constexpr int K2_TC = 32;          // cells per tile
 template <int SPW>
 __global__ void __launch_bounds__(1024, 1)
 rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant__ CUtensorMap rates_map, int ncell,
                   int nstage, const double* __restrict__ cellpar, const double* __restrict__ y,
                   double* __restrict__ ydot) {
   extern __shared__ __align__(128) unsigned char smb[];
-  const int n = net.n, R = net.R, NEQ = net.NEQ, RC = rc.RC, nchunk = rc.nchunk;
-  const int STG = (RC + 1) * (K2_TC * 8);                // bytes per stage: RC rows + one zero row
-  double* const ys = (double*)smb;                       // [n][16]
-  unsigned char* const kb0 = smb + (size_t)n * (K2_TC * 8);
+  const int NEQ = net.NEQ, RC = rc.RC, nchunk = rc.nchunk;
+  const int STG = (RC + 1) * 256;                        // bytes per stage: RC rows + one zero row
+  unsigned char* const kb0 = smb;
   uint64_t* const bars = (uint64_t*)(kb0 + (size_t)nstage * STG);
-  const int tid = threadIdx.x, cl = tid & (K2_TC - 1), hw = tid >> 4;     // hw: half-warp 0..63
-  const int ntile = (ncell + K2_TC - 1) / K2_TC;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int ntile = (ncell + 31) >> 5;
   const int my_tiles = (ntile > (int)blockIdx.x) ? (ntile - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int G = my_tiles * nchunk;                       // chunks this CTA will consume
   if (tid == 0) {
     for (int s2 = 0; s2 < nstage; ++s2) mbar_init(bars + s2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < K2_TC) for (int s2 = 0; s2 < nstage; ++s2) ((double*)(kb0 + (size_t)s2 * STG))[RC * K2_TC + tid] = 0.0;
+  if (tid < 32) for (int s2 = 0; s2 < nstage; ++s2) ((double*)(kb0 + (size_t)s2 * STG))[RC * 32 + tid] = 0.0;
   __syncthreads();
-  // producer (thread 0): chunk g of this CTA's stream -> stage g % nstage, RC/128 TMA boxes of 128 x 16
+  // producer (thread 0): chunk g of this CTA's stream -> stage g % nstage, RC/128 TMA boxes of 128 x 32
   auto issue = [&](int g) {
     const int ti = g / nchunk, c = g - ti * nchunk;
-    const int cell0 = ((int)blockIdx.x + ti * (int)gridDim.x) * K2_TC;
+    const int cell0 = ((int)blockIdx.x + ti * (int)gridDim.x) * 32;
     const int s2 = g % nstage;
-    mbar_expect_tx(bars + s2, (uint32_t)(RC * K2_TC * 8));    // whole boxes land, zero-filled where out of range
+    mbar_expect_tx(bars + s2, (uint32_t)(RC * 256));       // whole boxes land, zero-filled where out of range
     for (int b = 0; b < RC / 128; ++b)
-      tma_load_2d(kb0 + (size_t)s2 * STG + (size_t)b * 128 * (K2_TC * 8), &rates_map, cell0, c * RC + b * 128, bars + s2);
+      tma_load_2d(kb0 + (size_t)s2 * STG + (size_t)b * 128 * 256, &rates_map, cell0, c * RC + b * 128, bars + s2);
   };
   if (tid == 0) for (int g = 0; g < nstage - 1 && g < G; ++g) issue(g);
   for (int ti = 0; ti < my_tiles; ++ti) {
-    const int cell0 = ((int)blockIdx.x + ti * (int)gridDim.x) * K2_TC;
-    const int cell = cell0 + cl;
+    const int cell0 = ((int)blockIdx.x + ti * (int)gridDim.x) * 32;
+    const int cell = cell0 + lane;
     const bool ok = cell < ncell;
-    for (int i = hw; i < n; i += 64) ys[i * K2_TC + cl] = ok ? __ldcs(y + (size_t)i * ncell + cell) : 0.0;
+    const double* const yc = y + (ok ? cell : 0);          // this lane's column of y
     const double DS = ok ? cellpar[(size_t)RACG_P_ratioDust2HnucNum * ncell + cell] *
                            cellpar[(size_t)RACG_P_SitesPerGrain * ncell + cell] : 1.0;
     double acc[SPW];
 #pragma unroll
     for (int k = 0; k < SPW; ++k) acc[k] = 0.0;
-    __syncthreads();
     for (int c = 0; c < nchunk; ++c) {
       const int g = ti * nchunk + c, s2 = g % nstage;
       if (tid == 0 && g + nstage - 1 < G) {
@@ -210,53 +209,61 @@ rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant_
         issue(g + nstage - 1);
       }
       mbar_wait(bars + s2, (uint32_t)((g / nstage) & 1));
-      double* const kb = (double*)(kb0 + (size_t)s2 * STG) + cl;
-      // ---- fluxes in place (branches of chem_ode_f, src/disk.f90:4583-4643), one reaction per half-warp
-      for (int rl = hw; rl < RC; rl += 64) {
-        const int r = c * RC + rl;
-        double f = 0.0;
-        if (r < R) {
-          const uint32_t fwv = __ldg(net.fw + r);
-          const double k = kb[rl * K2_TC];
-          const int kind = (fwv >> 20) & 3;
-          const double y1 = ys[(fwv & 1023) * K2_TC + cl];
-          if (kind == FK_ONE) f = k * y1;
-          else if (kind == FK_TWO) {
-            const double y2 = ys[((fwv >> 10) & 1023) * K2_TC + cl];
-            f = k * y1 * y2;
-            if (y1 < 0.0 && y2 < 0.0) f = -f;
-          } else if (kind == FK_SAT) {
-            const double tmp1 = DS * net.sat_c[fwv >> 22];
-            if (tmp1 <= 0.0) f = k;
-            else { const double tmp = y1 / tmp1; f = (tmp <= 1e-4) ? k * tmp : k * (1.0 - exp(-tmp)); }
-          }
+      unsigned char* const kbb = kb0 + (size_t)s2 * STG + lane * 8;     // this lane's column of the stage
+      // ---- fluxes in place (branches of chem_ode_f, src/disk.f90:4583-4643), one reaction per warp
+      {
+        const int f0 = __ldg(rc.fl_off + 4 * c), f1 = __ldg(rc.fl_off + 4 * c + 1), f2 = __ldg(rc.fl_off + 4 * c + 2),
+                  f3 = __ldg(rc.fl_off + 4 * c + 3);
+        for (int i = f0 + w; i < f1; i += 32) {              // k * y1
+          const uint32_t v = __ldg(rc.flux + i);
+          double* kp = (double*)(kbb + (v & 511u) * 256);
+          *kp = *kp * __ldg(yc + (size_t)((v >> 9) & 1023u) * ncell);
         }
-        kb[rl * K2_TC] = f;
+        for (int i = f1 + w; i < f2; i += 32) {              // k * y1 * y2, sign as the reference
+          const uint32_t v = __ldg(rc.flux + i);
+          double* kp = (double*)(kbb + (v & 511u) * 256);
+          const double y1 = __ldg(yc + (size_t)((v >> 9) & 1023u) * ncell), y2 = __ldg(yc + (size_t)(v >> 19) * ncell);
+          double f = *kp * y1 * y2;
+          if (y1 < 0.0 && y2 < 0.0) f = -f;
+          *kp = f;
+        }
+        for (int i = f2 + w; i < f3; i += 32) {              // saturating desorption
+          const uint32_t v = __ldg(rc.flux + i);
+          double* kp = (double*)(kbb + (v & 511u) * 256);
+          const double k = *kp, y1 = __ldg(yc + (size_t)((v >> 9) & 1023u) * ncell);
+          const double tmp1 = DS * net.sat_c[v >> 19];
+          double f = k;
+          if (tmp1 > 0.0) { const double tmp = y1 / tmp1; f = (tmp <= 1e-4) ? k * tmp : k * (1.0 - exp(-tmp)); }
+          *kp = f;
+        }
       }
       __syncthreads();
-      // ---- this half-warp's species: run lists of the chunk
+      // ---- this warp's species: run lists of the chunk
       {
-        const uint32_t* p = rc.stream + __ldg(rc.off + hw * nchunk + c);
-        const int nr = __ldg(rc.nrun + hw * nchunk + c);
-        uint32_t nxt = __ldg(p);     // the stream is read one word ahead
-        int q = 0;
-        // runs are listed by ascending slot: a static walk over the slots keeps acc[] in registers
-#pragma unroll
-        for (int kk = 0; kk < SPW; ++kk) {
-          if (q < nr && (int)(nxt & 31u) == kk) {
-            const int nm = (nxt >> 5) & 0x1fff, np = nxt >> 18;
-            nxt = __ldg(++p);
-            double a = acc[kk];
-            for (int i = 0; i < nm; ++i) {
-              const uint32_t e = nxt; nxt = __ldg(++p);
-              a -= kb[(e & 0xffffu) * K2_TC]; a -= kb[(e >> 16) * K2_TC];
-            }
-            for (int i = 0; i < np; ++i) {
-              const uint32_t e = nxt; nxt = __ldg(++p);
-              a += kb[(e & 0xffffu) * K2_TC]; a += kb[(e >> 16) * K2_TC];
-            }
-            acc[kk] = a;
-            ++q;
+        const uint32_t* p = rc.stream + __ldg(rc.off + w * nchunk + c);
+        const int nr = __ldg(rc.nrun + w * nchunk + c);
+        const uint4* ep = (const uint4*)(p + ((nr + 3) & ~3));        // entries follow the padded headers
+        for (int q = 0; q < nr; ++q) {
+          const uint32_t h = __ldg(p + q);
+          const int k = h & 31, nm = (h >> 5) & 0x1fff, np = h >> 18;
+          double a = 0.0;
+          for (int i = 0; i < nm; ++i) {
+            const uint4 e = __ldg(ep++);
+            a -= *(const double*)(kbb + e.x); a -= *(const double*)(kbb + e.y);
+            a -= *(const double*)(kbb + e.z); a -= *(const double*)(kbb + e.w);
+          }
+          for (int i = 0; i < np; ++i) {
+            const uint4 e = __ldg(ep++);
+            a += *(const double*)(kbb + e.x); a += *(const double*)(kbb + e.y);
+            a += *(const double*)(kbb + e.z); a += *(const double*)(kbb + e.w);
+          }
+          switch (k) {     // uniform across the warp; keeps acc[] in registers
+#define K2_CASE(n) case n: if (n < SPW) acc[n < SPW ? n : 0] += a; break;
+            K2_CASE(0) K2_CASE(1) K2_CASE(2) K2_CASE(3) K2_CASE(4) K2_CASE(5) K2_CASE(6) K2_CASE(7)
+            K2_CASE(8) K2_CASE(9) K2_CASE(10) K2_CASE(11) K2_CASE(12) K2_CASE(13) K2_CASE(14) K2_CASE(15)
+            K2_CASE(16) K2_CASE(17) K2_CASE(18) K2_CASE(19) K2_CASE(20) K2_CASE(21) K2_CASE(22) K2_CASE(23)
+#undef K2_CASE
+            default: break;
           }
         }
       }
@@ -265,10 +272,10 @@ rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant_
     if (ok) {
 #pragma unroll
       for (int k = 0; k < SPW; ++k) {
-        const int sp = (k < rc.spw) ? __ldg(rc.slot_species + hw * rc.spw + k) : -1;
+        const int sp = (k < rc.spw) ? __ldg(rc.slot_species + w * rc.spw + k) : -1;
         if (sp >= 0) __stcs(ydot + (size_t)sp * ncell + cell, acc[k]);
       }
-      if (hw == 0) ydot[(size_t)(NEQ - 1) * ncell + cell] = 0.0;   // T slot, evolT = .false.
+      if (w == 0) ydot[(size_t)(NEQ - 1) * ncell + cell] = 0.0;   // T slot, evolT = .false.
     }
   }
 }
@@ -355,43 +362,54 @@ jac_kernel(const DevNet net, const JacColTables jc, int ncell, const double* __r
   }
 }
 
-// K3, wide variant (ncell % 4 == 0): a lane owns 4 consecutive cells (32-byte vector loads and
-// stores, 1 KB contiguous per warp access), a CTA of 32 warps a tile of 128 cells, so that every
-// Jacobian slot row is written in 1 KB pieces and each instruction moves 4x the bytes.
-struct D4 { double v[4]; };
-__device__ __forceinline__ D4 ld4(const double* p, bool ok) {
-  D4 r;
-  if (ok) { const double2 a = __ldg((const double2*)p), b = __ldg((const double2*)p + 1); r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; }
-  else { r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0; }
+// K3, wide variant (ncell % CPL == 0): a lane owns CPL consecutive cells (16- or 32-byte vector
+// loads and stores, 32*CPL*8 contiguous bytes per warp access); a CTA of NTH threads owns a tile of
+// 32*CPL cells.  <4, 1024>: one CTA per SM, every Jacobian slot row written in 1 KB pieces;
+// <2, 512>: two CTAs per SM, so that one CTA's derivative phase (global loads) overlaps the
+// other's gather/store phase across the group barriers.
+template <int CPL> struct DV { double v[CPL]; };
+template <int CPL>
+__device__ __forceinline__ DV<CPL> ldv(const double* p, bool ok) {
+  DV<CPL> r;
+  if (ok) {
+#pragma unroll
+    for (int q = 0; q < CPL; q += 2) { const double2 a = __ldg((const double2*)p + (q >> 1)); r.v[q] = a.x; r.v[q + 1] = a.y; }
+  } else {
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) r.v[q] = 0.0;
+  }
   return r;
 }
-__global__ void __launch_bounds__(1024)
-jac_kernel4(const DevNet net, const JacColTables jc, int ncell, const double* __restrict__ cellpar,
-            const double* __restrict__ y, const double* __restrict__ rates, double* __restrict__ pd) {
+template <int CPL, int NTH>
+__global__ void __launch_bounds__(NTH, 2048 / NTH > 2 ? 2 : 2048 / NTH / (CPL == 4 ? 2 : 1))
+jac_kernel_wide(const DevNet net, const JacColTables jc, int ncell, const double* __restrict__ cellpar,
+                const double* __restrict__ y, const double* __restrict__ rates, double* __restrict__ pd) {
   extern __shared__ __align__(16) double sm[];
-  const int NWARP = blockDim.x >> 5;
+  constexpr int TC = 32 * CPL;
+  const int NWARP = NTH >> 5;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  double* dbuf = sm;   // [max_pairs][128]
-  for (int tile = blockIdx.x; tile * 128 < ncell; tile += gridDim.x) {
-    const int cell = tile * 128 + 4 * l;
-    const bool ok = cell < ncell;          // ncell % 4 == 0: all four cells or none
-    const D4 a1 = ld4(cellpar + (size_t)RACG_P_ratioDust2HnucNum * ncell + cell, ok);
-    const D4 a2 = ld4(cellpar + (size_t)RACG_P_SitesPerGrain * ncell + cell, ok);
-    double DS[4];
+  double* dbuf = sm;   // [max_pairs][TC]
+  for (int tile = blockIdx.x; tile * TC < ncell; tile += gridDim.x) {
+    const int cell = tile * TC + CPL * l;
+    const bool ok = cell < ncell;          // ncell % CPL == 0: all cells of a lane or none
+    const DV<CPL> a1 = ldv<CPL>(cellpar + (size_t)RACG_P_ratioDust2HnucNum * ncell + cell, ok);
+    const DV<CPL> a2 = ldv<CPL>(cellpar + (size_t)RACG_P_SitesPerGrain * ncell + cell, ok);
+    double DS[CPL];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) DS[q] = ok ? a1.v[q] * a2.v[q] : 1.0;
+    for (int q = 0; q < CPL; ++q) DS[q] = ok ? a1.v[q] * a2.v[q] : 1.0;
     if (ok) {
       const double2 z2 = make_double2(0.0, 0.0);
       for (int z = w; z < jc.nzero; z += NWARP) {
         double2* o = (double2*)(pd + (size_t)jc.zero_slots[z] * ncell + cell);
-        __stcs(o, z2); __stcs(o + 1, z2);
+#pragma unroll
+        for (int q = 0; q < CPL / 2; ++q) __stcs(o + q, z2);
       }
     }
     for (int g = 0; g < jc.ngroups; ++g) {
       __syncthreads();
       const int pb = jc.grp_pair_ptr[g], pe = jc.grp_pair_ptr[g + 1];
       for (int p0 = pb + w; p0 < pe; p0 += 2 * NWARP) {
-        uint32_t fwv2[2]; int which2[2]; D4 k2[2], ya2[2], yb2[2];
+        uint32_t fwv2[2]; int which2[2]; DV<CPL> k2[2], ya2[2], yb2[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int p = p0 + u * NWARP;
@@ -402,9 +420,9 @@ jac_kernel4(const DevNet net, const JacColTables jc, int ncell, const double* __
           fwv2[u] = on ? __ldg(net.fw + r) : (3u << 20);
           const int kind = (fwv2[u] >> 20) & 3;
           const int r1 = fwv2[u] & 1023, r2 = (fwv2[u] >> 10) & 1023;
-          k2[u] = ld4(rates + (size_t)r * ncell + cell, on && ok);
-          ya2[u] = ld4(y + (size_t)r1 * ncell + cell, on && ok && kind != FK_ONE);
-          yb2[u] = (kind == FK_TWO && r2 != r1) ? ld4(y + (size_t)r2 * ncell + cell, on && ok) : ya2[u];
+          k2[u] = ldv<CPL>(rates + (size_t)r * ncell + cell, on && ok);
+          ya2[u] = ldv<CPL>(y + (size_t)r1 * ncell + cell, on && ok && kind != FK_ONE);
+          yb2[u] = (kind == FK_TWO && r2 != r1) ? ldv<CPL>(y + (size_t)r2 * ncell + cell, on && ok) : ya2[u];
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -413,29 +431,40 @@ jac_kernel4(const DevNet net, const JacColTables jc, int ncell, const double* __
           const uint32_t fwv = fwv2[u];
           const int kind = (fwv >> 20) & 3, which = which2[u];
           const int r1 = fwv & 1023, r2 = (fwv >> 10) & 1023;
-          double d[4];
+          double d[CPL];
+          if (kind == FK_ONE) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double k = k2[u].v[q];
-            double dd = 0.0;
-            if (kind == FK_ONE) dd = k;
-            else if (kind == FK_TWO) {
+            for (int q = 0; q < CPL; ++q) d[q] = k2[u].v[q];
+          } else if (kind == FK_TWO) {
+            // d(k y1 y2)/dy: the other factor (both factors when r1 == r2), sign as chem_ode_jac
+            const bool same = r1 == r2;
+            const double fac = same ? 2.0 : 1.0;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
               const double y1 = ya2[u].v[q], y2 = yb2[u].v[q];
-              if (r1 != r2) dd = (which == 0) ? k * y2 : k * y1;
-              else dd = 2.0 * k * y2;
+              double dd = fac * k2[u].v[q] * ((same || which == 0) ? y2 : y1);
               if (y1 < 0.0 && y2 < 0.0) dd = -dd;
-            } else if (kind == FK_SAT) {
+              d[q] = dd;
+            }
+          } else if (kind == FK_SAT) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+              double dd = 0.0;
               const double tmp2 = DS[q] * net.sat_c[fwv >> 22];
               if (tmp2 > 0.0) {
                 const double tmp1 = 1.0 / tmp2;
                 const double tmp = ya2[u].v[q] * tmp1;
-                dd = (tmp <= 1e-4) ? k * tmp1 : k * tmp1 * exp(-tmp);
+                dd = (tmp <= 1e-4) ? k2[u].v[q] * tmp1 : k2[u].v[q] * tmp1 * exp(-tmp);
               }
+              d[q] = dd;
             }
-            d[q] = dd;
+          } else {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) d[q] = 0.0;
           }
-          double2* o = (double2*)(dbuf + (size_t)(p - pb) * 128 + 4 * l);
-          o[0] = make_double2(d[0], d[1]); o[1] = make_double2(d[2], d[3]);
+          double2* o = (double2*)(dbuf + (size_t)(p - pb) * TC + CPL * l);
+#pragma unroll
+          for (int q = 0; q < CPL; q += 2) o[q >> 1] = make_double2(d[q], d[q + 1]);
         }
       }
       __syncthreads();
@@ -445,17 +474,23 @@ jac_kernel4(const DevNet net, const JacColTables jc, int ncell, const double* __
         const int slot = __ldg(jc.slot_id + s), e0 = __ldg(jc.slot_ent_ptr + s), e1 = __ldg(jc.slot_ent_ptr + s + 1);
         double* op = pd + (size_t)slot * ncell + cell;
         // coherent read (not the read-only path): an earlier group of this kernel stored the value
-        D4 acc;
-        if (accum && ok) { const double2 a = __ldcg((const double2*)op), b2 = __ldcg((const double2*)op + 1); acc.v[0] = a.x; acc.v[1] = a.y; acc.v[2] = b2.x; acc.v[3] = b2.y; }
-        else { acc.v[0] = acc.v[1] = acc.v[2] = acc.v[3] = 0.0; }
+        double acc[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; q += 2) {
+          if (accum && ok) { const double2 a = __ldcg((const double2*)op + (q >> 1)); acc[q] = a.x; acc[q + 1] = a.y; }
+          else { acc[q] = 0.0; acc[q + 1] = 0.0; }
+        }
         for (int e = e0; e < e1; ++e) {
           const uint32_t v = __ldg(jc.ent + e);
           const double cf = (double)((int)(v >> 24) - 4);
-          const double2* dp = (const double2*)(dbuf + (size_t)(v & 0xffffffu) * 128 + 4 * l);
-          const double2 da = dp[0], db = dp[1];
-          acc.v[0] += cf * da.x; acc.v[1] += cf * da.y; acc.v[2] += cf * db.x; acc.v[3] += cf * db.y;
+          const double2* dp = (const double2*)(dbuf + (size_t)(v & 0xffffffu) * TC + CPL * l);
+#pragma unroll
+          for (int q = 0; q < CPL; q += 2) { const double2 da = dp[q >> 1]; acc[q] += cf * da.x; acc[q + 1] += cf * da.y; }
         }
-        if (ok) { __stcs((double2*)op, make_double2(acc.v[0], acc.v[1])); __stcs((double2*)op + 1, make_double2(acc.v[2], acc.v[3])); }
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < CPL; q += 2) __stcs((double2*)op + (q >> 1), make_double2(acc[q], acc[q + 1]));
+        }
       }
     }
   }
@@ -496,25 +531,24 @@ static bool make_rates_map(CUtensorMap* map, const double* rates, int R, int nce
 
 cudaError_t launch_rhs(const DevNet& net, const RhsChunkDev& rc, int ncell, const double* cellpar, const double* y,
                        const double* rates, double* ydot, int nsm, cudaStream_t st) {
-  // streaming variant: the tensor map needs a 16-byte row pitch and base (even ncell); <= 16 species per half-warp
-  if (rc.spw <= 16 && rc.RC % 128 == 0 && rc.RC < 65535 && (ncell & 1) == 0 && ((size_t)rates & 15) == 0) {
-    const size_t stg = (size_t)(rc.RC + 1) * (K2_TC * 8), ybytes = (size_t)net.n * (K2_TC * 8);
-    int nstage = (int)((227 * 1024 - 256 - ybytes) / stg);
-    if (nstage > 3) nstage = 3;
+  // streaming variant: the tensor map needs a 16-byte row pitch and base (even ncell); <= 24 species per warp
+  if (rc.spw <= 24 && rc.RC % 128 == 0 && rc.RC <= 512 && (ncell & 1) == 0 && ((size_t)rates & 15) == 0) {
+    const size_t stg = (size_t)(rc.RC + 1) * 256;
+    const int nstage = 2;
     CUtensorMap map;
-    if (nstage >= 2 && make_rates_map(&map, rates, net.R, ncell)) {
-      const size_t smem2 = ybytes + nstage * stg + 64;
+    if (nstage * stg + 64 <= 227 * 1024 && make_rates_map(&map, rates, net.R, ncell)) {
+      const size_t smem2 = nstage * stg + 64;
       const int ntile = (ncell + K2_TC - 1) / K2_TC;
       const int grid = ntile < nsm ? ntile : nsm;
       cudaError_t e2;
-      if (rc.spw <= 8) {
-        e2 = cudaFuncSetAttribute(rhs_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        if (e2 != cudaSuccess) return e2;
-        rhs_stream_kernel<8><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
-      } else {
+      if (rc.spw <= 16) {
         e2 = cudaFuncSetAttribute(rhs_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e2 != cudaSuccess) return e2;
         rhs_stream_kernel<16><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
+      } else {
+        e2 = cudaFuncSetAttribute(rhs_stream_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) return e2;
+        rhs_stream_kernel<24><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
       }
       return cudaGetLastError();
     }
@@ -530,16 +564,27 @@ cudaError_t launch_rhs(const DevNet& net, const RhsChunkDev& rc, int ncell, cons
   return cudaGetLastError();
 }
 
+int g_k3_variant = 2;   // 2: two 64-cell CTAs per SM (default), 4: one 128-cell CTA per SM (A/B measurements)
 cudaError_t launch_jac(const DevNet& net, const JacColTables& jc, int ncell, const double* cellpar, const double* y,
                        const double* rates, double* pd, int nsm, cudaStream_t st) {
+  const bool aligned = ((size_t)pd % 32) == 0 && ((size_t)y % 32) == 0 && ((size_t)rates % 32) == 0 && ((size_t)cellpar % 32) == 0;
+  // two 64-cell CTAs per SM (lane = 2 cells) when their derivative buffers fit side by side
+  const size_t smem2 = (size_t)jc.max_pairs * 64 * sizeof(double);
+  if (g_k3_variant != 4 && ncell % 2 == 0 && aligned && (smem2 + 1024) * 2 <= 227 * 1024) {
+    auto kern = jac_kernel_wide<2, 512>;
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 != cudaSuccess) return e2;
+    const int ntiles = (ncell + 63) / 64;
+    kern<<<ntiles < 2 * nsm ? ntiles : 2 * nsm, 512, smem2, st>>>(net, jc, ncell, cellpar, y, rates, pd);
+    return cudaGetLastError();
+  }
   const size_t smem4 = (size_t)jc.max_pairs * 128 * sizeof(double);
-  if (ncell % 4 == 0 && smem4 <= 226 * 1024 && ((size_t)pd % 32) == 0 && ((size_t)y % 32) == 0 &&
-      ((size_t)rates % 32) == 0 && ((size_t)cellpar % 32) == 0) {
-    cudaError_t e4 = cudaFuncSetAttribute(jac_kernel4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+  if (ncell % 4 == 0 && smem4 <= 226 * 1024 && aligned) {
+    auto kern = jac_kernel_wide<4, 1024>;
+    cudaError_t e4 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
     if (e4 != cudaSuccess) return e4;
     const int ntiles4 = (ncell + 127) / 128;
-    const int per_sm4 = (smem4 + 1024) * 2 <= 227 * 1024 ? 2 : 1;
-    jac_kernel4<<<ntiles4 < nsm * per_sm4 ? ntiles4 : nsm * per_sm4, 1024, smem4, st>>>(net, jc, ncell, cellpar, y, rates, pd);
+    kern<<<ntiles4 < nsm ? ntiles4 : nsm, 1024, smem4, st>>>(net, jc, ncell, cellpar, y, rates, pd);
     return cudaGetLastError();
   }
   const size_t smem = (size_t)jc.max_pairs * 32 * sizeof(double);

@@ -29,6 +29,7 @@ cudaError_t launch_integrate(const DevNet& net, unsigned long long net_id, int d
 cudaError_t launch_cost_order(int ncell, const double* stats, float* cost, int* order, int* hist, cudaStream_t st);
 cudaError_t launch_cost(int ncell, const double* stats, float* cost, cudaStream_t st);
 // racg_batch.cu
+extern int g_k3_variant;
 cudaError_t launch_rates(const DevNet& net, int ncell, const double* cellpar, double* rates, cudaStream_t st);
 cudaError_t launch_rhs(const DevNet& net, const RhsChunkDev& rc, int ncell, const double* cellpar, const double* y,
                        const double* rates, double* ydot, int nsm, cudaStream_t st);
@@ -268,6 +269,8 @@ static int create_ctx(racg_handle* h, int device, DevCtx** out) {
     if ((rc = upload(c, s.off, &r.off))) return rc;
     if ((rc = upload(c, s.nrun, &r.nrun))) return rc;
     if ((rc = upload(c, s.stream, &r.stream))) return rc;
+    if ((rc = upload(c, s.fl_off, &r.fl_off))) return rc;
+    if ((rc = upload(c, s.flux, &r.flux))) return rc;
   }
   {
     JacColTables& jc = c->jc;
@@ -473,6 +476,7 @@ int racg_set_option(racg_handle* h, const char* name, double value) {
   const std::string k = name;
   if (k == "warm_order") h->warm_order = value != 0.0;
   else if (k == "level_lu") h->level_lu = value != 0.0;
+  else if (k == "k3_variant") { g_k3_variant = (int)value; return 0; }   // process-wide, diagnostics
   else return fail(RACG_ERR_ARG, "unknown option: " + k);
   if (k != "warm_order" && !h->dev.empty()) {
     DeviceGuard guard;

@@ -128,6 +128,7 @@ struct BatchArgs {
 struct RhsChunkDev {
   int RC, nchunk, spw;
   const int* slot_species; const uint32_t* off; const int* nrun; const uint32_t* stream;
+  const int* fl_off; const uint32_t* flux;
 };
 
 // stand-alone K3 column-group schedule (racg_batch.cu)

@@ -236,12 +236,8 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   // ---- streaming K2 schedule (HostNet::RhsChunks)
   {
     HostNet::RhsChunks& rc = hn.rhsc;
-    // chunk size: two stages of (RC + 1) x 128 B beside the y tile of N x 128 B in 227 KB
-    rc.RC = ((int)((231000 - (long)N * 128) / 256) - 1) / 128 * 128;
-    if (rc.RC > 640) rc.RC = 640;
-    if (rc.RC < 128) rc.RC = 128;
-    rc.nchunk = (R + rc.RC - 1) / rc.RC; rc.nwarp = 64; rc.spw = (N + rc.nwarp - 1) / rc.nwarp;
-    // species -> (half-warp, slot): heaviest species first onto the least loaded owner with a free slot
+    rc.RC = 384; rc.nchunk = (R + rc.RC - 1) / rc.RC; rc.nwarp = 32; rc.spw = (N + rc.nwarp - 1) / rc.nwarp;
+    // species -> (warp, slot): heaviest species first onto the least loaded warp with a free slot
     std::vector<int> order(N);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sp_rows[a].size() > sp_rows[b].size(); });
@@ -254,31 +250,53 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
       rc.slot_species[(size_t)best * rc.spw + used[best]++] = sp;
       load[best] += (long)sp_rows[sp].size() + 4 * rc.nchunk;
     }
+    // run lists: entries are byte offsets of the chunk's rows (row pitch 256 B), 4 per 16-byte group
     rc.off.assign((size_t)rc.nwarp * rc.nchunk, 0); rc.nrun.assign((size_t)rc.nwarp * rc.nchunk, 0);
     for (int w = 0; w < rc.nwarp; ++w)
       for (int c = 0; c < rc.nchunk; ++c) {
+        while (rc.stream.size() % 4) rc.stream.push_back(0u);
         rc.off[(size_t)w * rc.nchunk + c] = (uint32_t)rc.stream.size();
         int nrun = 0;
+        std::vector<uint32_t> hdr, ent;
         for (int k = 0; k < rc.spw; ++k) {
           const int sp = rc.slot_species[(size_t)w * rc.spw + k];
           if (sp < 0) continue;
-          std::vector<uint16_t> em, ep;
+          std::vector<uint32_t> em, ep;
           for (auto& e : sp_rows[sp]) {
             if (e.first / rc.RC != c) continue;
-            const int loc = e.first % rc.RC;
-            for (int m = 0; m < std::abs(e.second); ++m) (e.second < 0 ? em : ep).push_back((uint16_t)loc);
+            const uint32_t loc = (uint32_t)(e.first % rc.RC) * 256u;
+            for (int m = 0; m < std::abs(e.second); ++m) (e.second < 0 ? em : ep).push_back(loc);
           }
           if (em.empty() && ep.empty()) continue;
-          if (em.size() % 2) em.push_back((uint16_t)rc.RC);
-          if (ep.size() % 2) ep.push_back((uint16_t)rc.RC);
-          rc.stream.push_back((uint32_t)k | ((uint32_t)(em.size() / 2) << 5) | ((uint32_t)(ep.size() / 2) << 18));
-          for (size_t q = 0; q < em.size(); q += 2) rc.stream.push_back((uint32_t)em[q] | ((uint32_t)em[q + 1] << 16));
-          for (size_t q = 0; q < ep.size(); q += 2) rc.stream.push_back((uint32_t)ep[q] | ((uint32_t)ep[q + 1] << 16));
+          while (em.size() % 4) em.push_back((uint32_t)rc.RC * 256u);
+          while (ep.size() % 4) ep.push_back((uint32_t)rc.RC * 256u);
+          hdr.push_back((uint32_t)k | ((uint32_t)(em.size() / 4) << 5) | ((uint32_t)(ep.size() / 4) << 18));
+          ent.insert(ent.end(), em.begin(), em.end());
+          ent.insert(ent.end(), ep.begin(), ep.end());
           ++nrun;
         }
+        // layout of one (warp, chunk) list: headers padded to a multiple of 4 words, then the entries
+        while (hdr.size() % 4) hdr.push_back(0u);
+        rc.stream.insert(rc.stream.end(), hdr.begin(), hdr.end());
+        rc.stream.insert(rc.stream.end(), ent.begin(), ent.end());
         rc.nrun[(size_t)w * rc.nchunk + c] = nrun;
       }
-    rc.stream.push_back(0u);   // the kernel reads one word ahead
+    for (int q = 0; q < 8; ++q) rc.stream.push_back(0u);
+    // flux lists per chunk, sorted by kind: word = local row | r1 << 9 | (r2 or saturation index) << 19
+    rc.fl_off.assign((size_t)rc.nchunk * 4, 0);
+    for (int c = 0; c < rc.nchunk; ++c) {
+      for (int kind = 0; kind < 3; ++kind) {
+        rc.fl_off[(size_t)c * 4 + kind] = (int)rc.flux.size();
+        for (int i = c * rc.RC; i < std::min(R, (c + 1) * rc.RC); ++i) {
+          const uint32_t w = hn.fw[i];
+          if ((int)((w >> 20) & 3) != kind) continue;
+          const uint32_t second = (kind == FK_SAT) ? (w >> 22) : ((w >> 10) & 1023u);
+          rc.flux.push_back((uint32_t)(i - c * rc.RC) | ((w & 1023u) << 9) | (second << 19));
+        }
+      }
+      rc.fl_off[(size_t)c * 4 + 3] = (int)rc.flux.size();
+    }
+    rc.flux.push_back(0u);
   }
 
   // ---- species-block pattern and fill-reducing ordering

@@ -138,19 +138,24 @@ struct HostNet {
   } ss;
 
   // ---- stand-alone K2, streaming variant (racg_batch.cu rhs_stream_kernel): reactions in chunks of
-  // RC rows whose rate coefficients arrive by TMA tile loads; the 64 half-warps of a CTA each own up
-  // to SPW species of a 16-cell tile (accumulators in registers).  Per (half-warp, chunk) a run list:
-  //   header word  = slot | n_minus_words << 5 | n_plus_words << 18
-  //   entry words  = 2 chunk-local reaction ids per word (padding id = RC: a zero row), first the
-  //                  consumed (-) then the produced (+) terms of the species inside the chunk, each in
-  //                  reaction order; a coefficient of magnitude m is m entries (as the reference's
-  //                  loop subtracts/adds the flux once per occurrence, src/disk.f90:4644-4650)
+  // RC rows whose rate coefficients arrive by TMA tile loads; the 32 warps of a CTA each own up to
+  // SPW species of a 32-cell tile (accumulators in registers).
+  //   flux lists   per chunk the reactions sorted by flux kind (FK_ONE, FK_TWO, FK_SAT):
+  //                word = chunk-local row | r1 << 9 | (r2 or saturation index) << 19
+  //   run lists    per (warp, chunk): header words (slot | n_minus_groups << 5 | n_plus_groups << 18,
+  //                padded to a multiple of 4), then the entries: byte offsets of the chunk's rows
+  //                (row pitch 256 B; padding = the zero row RC) in groups of 4, per run first the
+  //                consumed (-) then the produced (+) terms of the species inside the chunk, each in
+  //                reaction order; a coefficient of magnitude m is m entries (as the reference's
+  //                loop subtracts/adds the flux once per occurrence, src/disk.f90:4644-4650)
   struct RhsChunks {
-    int RC = 0, nchunk = 0, nwarp = 64, spw = 0;   // nwarp = owners (half-warps)
+    int RC = 0, nchunk = 0, nwarp = 32, spw = 0;
     std::vector<int> slot_species;      // [nwarp*spw] species id or -1
-    std::vector<uint32_t> off;          // [nwarp*nchunk] offset of the run list in stream
+    std::vector<uint32_t> off;          // [nwarp*nchunk] offset of the run list in stream (multiple of 4)
     std::vector<int> nrun;              // [nwarp*nchunk]
     std::vector<uint32_t> stream;
+    std::vector<int> fl_off;            // [nchunk*4] start of the ONE / TWO / SAT lists of the chunk, end
+    std::vector<uint32_t> flux;
   } rhsc;
   // ---- Jacobian gather into the storage index space, two passes (d/dy_r1, d/dy_r2) ----
   Gather jac[2];
