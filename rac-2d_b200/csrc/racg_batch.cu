@@ -214,11 +214,13 @@ rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant_
       {
         const int f0 = __ldg(rc.fl_off + 4 * c), f1 = __ldg(rc.fl_off + 4 * c + 1), f2 = __ldg(rc.fl_off + 4 * c + 2),
                   f3 = __ldg(rc.fl_off + 4 * c + 3);
+#pragma unroll 4
         for (int i = f0 + w; i < f1; i += 32) {              // k * y1
           const uint32_t v = __ldg(rc.flux + i);
           double* kp = (double*)(kbb + (v & 511u) * 256);
           *kp = *kp * __ldg(yc + (size_t)((v >> 9) & 1023u) * ncell);
         }
+#pragma unroll 4
         for (int i = f1 + w; i < f2; i += 32) {              // k * y1 * y2, sign as the reference
           const uint32_t v = __ldg(rc.flux + i);
           double* kp = (double*)(kbb + (v & 511u) * 256);
