@@ -1,4 +1,5 @@
 mkdir -p gpurun_out/r2
-timeout 180 python tests/gpu_kernels_bw.py > gpurun_out/r2/kernels_bw14.log 2>&1; echo "bw rc=$?"
-cat gpurun_out/r2/kernels_bw14.log
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "rhs_jac" --timeout 300 2>&1 | tail -3
+timeout 1200 python bench.py > gpurun_out/r2/bench_final.json 2> gpurun_out/r2/bench_final.err; echo "bench rc=$?"
+tail -c 600 gpurun_out/r2/bench_final.json; tail -3 gpurun_out/r2/bench_final.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2/bench_ref.json 2> gpurun_out/r2/bench_ref.err; echo "ref rc=$?"
+head -c 300 gpurun_out/r2/bench_ref.json
