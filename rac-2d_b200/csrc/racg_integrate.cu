@@ -444,19 +444,26 @@ __device__ __noinline__ void warp_trisolve_lower(int t_off, int ld, int nt, int 
     const double* col = T + base * ld + base + l;
 #pragma unroll 1
     for (int c0 = 0; c0 < cmax; c0 += 8) {
-      double a[WIN][8];
+      double a[WIN][8], l10[4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a[0][j] = (on[0] && l > c0 + j) ? col[j * ld] : 0.0;
 #pragma unroll
         for (int m = 1; m < WIN; ++m) a[m][j] = on[m] ? col[j * ld + 32 * m] : 0.0;
       }
+      // columns go in pairs: both right-hand-side values are shuffled at once and every lane forms
+      // the second unknown itself, x_{c+1} = b_{c+1} - L(c+1,c) x_c (bit-identical to what its owner
+      // computes), so the dependent chain per PAIR is one shuffle and two FMAs
+#pragma unroll
+      for (int q = 0; q < 4; ++q) l10[q] = T[(base + c0 + 2 * q) * ld + base + c0 + 2 * q + 1];
       col += 8 * ld;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double xc = __shfl_sync(0xffffffffu, x[0], c0 + j);
+      for (int q = 0; q < 4; ++q) {
+        const double xc = __shfl_sync(0xffffffffu, x[0], c0 + 2 * q);
+        const double x1p = __shfl_sync(0xffffffffu, x[0], c0 + 2 * q + 1);
+        const double x1f = x1p - l10[q] * xc;
 #pragma unroll
-        for (int m = 0; m < WIN; ++m) x[m] -= a[m][j] * xc;
+        for (int m = 0; m < WIN; ++m) { x[m] -= a[m][2 * q] * xc; x[m] -= a[m][2 * q + 1] * x1f; }
       }
     }
     if (on[0]) xs[base + l] = x[0];
@@ -486,19 +493,25 @@ __device__ __noinline__ void warp_trisolve_upper(int t_off, int ld, int nt, int 
     const double* col = T + (base + cmax - 8) * ld + base + l;
 #pragma unroll 1
     for (int c0 = cmax - 8; c0 >= 0; c0 -= 8) {
-      double a[WIN][8];
+      double a[WIN][8], u10[4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a[0][j] = (l < c0 + j) ? col[j * ld] * rdl : 0.0;
 #pragma unroll
         for (int m = 1; m < WIN; ++m) a[m][j] = (mb >= m) ? col[j * ld - 32 * m] : 0.0;
       }
+      // pairs of columns (c, c-1) as in the forward sweep: x_{c-1} = s_{c-1} - (U(c-1,c) rd_{c-1}) x_c
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        u10[q] = T[(base + c0 + 2 * q + 1) * ld + base + c0 + 2 * q] * rd[base + c0 + 2 * q];
       col -= 8 * ld;
 #pragma unroll
-      for (int j = 7; j >= 0; --j) {
-        const double xc = __shfl_sync(0xffffffffu, x[0], c0 + j);
+      for (int q = 3; q >= 0; --q) {
+        const double xc = __shfl_sync(0xffffffffu, x[0], c0 + 2 * q + 1);
+        const double x1p = __shfl_sync(0xffffffffu, x[0], c0 + 2 * q);
+        const double x1f = x1p - u10[q] * xc;
 #pragma unroll
-        for (int m = 0; m < WIN; ++m) x[m] -= a[m][j] * xc;
+        for (int m = 0; m < WIN; ++m) { x[m] -= a[m][2 * q + 1] * xc; x[m] -= a[m][2 * q] * x1f; }
       }
     }
     if (base + l < nt) xs[base + l] = x[0];
