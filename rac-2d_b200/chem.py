@@ -383,5 +383,6 @@ class ChemSolver:
         _check(lib().racg_phase_cycles(self.h, _p(out)))
         names = ["rates", "f", "jac", "fact_head", "fact_schur", "fact_tail", "solve", "vec", "glu_loop",
                  "total", "ncell", "pbuild", "tail_inv", "solve_fwd", "solve_tail", "solve_bwd",
-                 "f_flux", "f_gather", "glu_pivmul", "glu_flat", "glu_narrow", "glu_wide", "solve_spmv", "glu_copy"]
+                 "f_flux", "f_gather", "glu_pivmul", "glu_flat", "glu_narrow", "glu_wide", "solve_spmv", "glu_copy",
+                 "tail_L0", "tail_Lall", "tail_w0mid", "tail_U0", "tail_Utop", "blk_diag", "blk_panel", "blk_update"]
         return {n: out[i] for i, n in enumerate(names)}

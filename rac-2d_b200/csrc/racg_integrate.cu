@@ -56,7 +56,8 @@ __device__ __forceinline__ long long pclock() { return 0; }
 
 enum Phase { PH_RATES = 0, PH_F, PH_JAC, PH_FACT_HEAD, PH_FACT_SCHUR, PH_FACT_TAIL, PH_SOLVE,
              PH_VEC, PH_G_LOOP, PH_TOTAL, PH_NCELL, PH_PBUILD, PH_TAILINV, PH_S_FWD, PH_S_TAIL, PH_S_BWD,
-             PH_F_FLUX, PH_F_GATHER, PH_G_PIVMUL, PH_G_FLAT, PH_G_NARROW, PH_G_WIDE, PH_S_SPMV, PH_G_COPY, PH_COUNT };
+             PH_F_FLUX, PH_F_GATHER, PH_G_PIVMUL, PH_G_FLAT, PH_G_NARROW, PH_G_WIDE, PH_S_SPMV, PH_G_COPY,
+             PH_T_L0, PH_T_LALL, PH_T_W0MID, PH_T_U0, PH_T_UTOP, PH_B_DIAG, PH_B_PANEL, PH_B_UPD, PH_COUNT };
 
 struct Smem {
   double* y;      // [n]  argument of f / right-hand side and result of the linear solve
@@ -366,8 +367,151 @@ __device__ __forceinline__ void tail_step(double (&t)[TL][TC], int k, int ti, in
   }
 }
 
+// ---------------------------------------------------------------------------
+// Blocked variant of the dense tail LU (256 threads, 16 x 16 grid): right-looking with 16-column
+// panels.  The one-pivot-per-barrier scheme below spends ~950 cycles per pivot on two barriers,
+// two shared-memory round trips and a division; here a pivot costs one shuffle round inside a
+// single warp, and the other 112 x 112 x 16 multiply-adds of a panel run without barriers:
+//   1. diag16_lu     warp 0 factors the 16 x 16 diagonal block, one row per lane, pivot row by shuffles
+//   2. panel_solve   threads 0.. solve the rows of L21 = A21 U11^-1, threads 128.. the columns of
+//                    U12 = L11^-1 A12 (16 unknowns each, operands broadcast from shared memory)
+//   3. trailing update A22 -= L21 U12 on the register tiles (16 k-steps, no barrier), then only the
+//      next panel's column and row slices go back to shared memory
+// Every element receives the same multiply-adds in the same order (k ascending, l = a * (1/pivot))
+// as in the unblocked scheme: the factor is bit-identical.
+// (LD = leading dimension of the tail block = nt + 1, a compile-time constant of the TL variant:
+// every shared-memory access below is base register + immediate)
+template <int LD>
+__device__ __noinline__ void diag16_lu(int blk_off, int rd_off, int row_off, int* flag) {
+  constexpr int ld = LD;
+  double* const B = smem_raw + blk_off;
+  double* const rdt = smem_raw + rd_off;
+  double* const rowbuf = smem_raw + row_off;      // 2 x 16 doubles, 16-byte aligned
+  const int l = threadIdx.x & 31, i = l & 15;
+  double r[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) r[j] = B[j * ld + i];
+  // The pivot row goes through shared memory (one store by its owner, broadcast loads by all):
+  // a shuffle costs ~8 issue cycles per 32-bit half on this part, 30 of them per pivot were the
+  // whole cost of this routine.
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    double2* const rb = (double2*)(rowbuf + 16 * (k & 1));
+    if (l == k) {
+#pragma unroll
+      for (int j = (k & ~1); j < 16; j += 2) rb[j >> 1] = make_double2(r[j], r[j + 1]);
+    }
+    __syncwarp();
+    double u[16];
+#pragma unroll
+    for (int j = (k & ~1); j < 16; j += 2) { const double2 v = rb[j >> 1]; u[j] = v.x; u[j + 1] = v.y; }
+    const double piv = u[k];
+    if (piv == 0.0 || isnan(piv)) { if (l == 0) *flag = 1; }
+    const double inv = 1.0 / piv;
+    if (l == 0) rdt[k] = inv;     // 1 / U(k,k) for the back substitution
+    const double m = r[k] * inv;
+    if (i > k) {
+      r[k] = m;
+#pragma unroll
+      for (int j = k + 1; j < 16; ++j) r[j] -= m * u[j];
+    }
+  }
+  if (l < 16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) B[j * ld + i] = r[j];
+  }
+}
+template <int LD>
+__device__ __noinline__ void panel_solve(int dt_off, int c0, int rd_off) {
+  constexpr int ld = LD, nt = LD - 1;
+  double* const Dt = smem_raw + dt_off;
+  const double* const rd = smem_raw + rd_off;     // rd[j] = 1 / U(c0+j, c0+j)
+  const int tid = threadIdx.x, nrem = nt - c0 - 16;
+  const double* const D = Dt + c0 * ld + c0;      // the factored diagonal block
+  if (tid < nrem) {                               // one row of L21
+    double* const row = Dt + c0 * ld + c0 + 16 + tid;
+    double x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = row[j * ld];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      double s = x[j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= x[k] * D[j * ld + k];
+      x[j] = s * rd[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) row[j * ld] = x[j];
+  } else if (tid >= 128 && tid < 128 + nrem) {    // one column of U12
+    double* const col = Dt + (c0 + 16 + tid - 128) * ld + c0;
+    double x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = col[k];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      double s = x[k];
+#pragma unroll
+      for (int m = 0; m < k; ++m) s -= D[m * ld + k] * x[m];
+      x[k] = s;
+    }
+#pragma unroll
+    for (int k = 1; k < 16; ++k) col[k] = x[k];
+  }
+}
 template <int TL>
-__device__ __noinline__ void tail_lu(int dt_off, int pub_off, int* flag) {   // reciprocal pivots -> dinv[nh + k]
+__device__ __forceinline__ void tail_lu_blocked(int dt_off, int pub_off, int* flag, unsigned long long* ph) {
+  const DevNet& net = c_net;
+  constexpr int ld = 16 * TL + 1;      // = net.ldt (checked at launch)
+  const int rd_off = 2 * net.n + net.nh;
+  double* const Dt = smem_raw + dt_off;
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  double t[TL][TL];      // rows ti + 16 a, columns tj + 16 b; the first block row / column never enters registers
+#pragma unroll
+  for (int a = 1; a < TL; ++a)
+#pragma unroll
+    for (int b = 1; b < TL; ++b) t[a][b] = Dt[(tj + 16 * b) * ld + ti + 16 * a];
+#pragma unroll
+  for (int p = 0; p < TL; ++p) {
+    const int c0 = 16 * p;
+    const long long tb0 = pclock();
+    if (threadIdx.x < 32) diag16_lu<ld>(dt_off + c0 * ld + c0, rd_off + c0, (pub_off + 1) & ~1, flag);
+    if (RACG_PHASE_TIMERS && threadIdx.x == 0) ph[PH_B_DIAG] += pclock() - tb0;
+    if (p < TL - 1) {
+      __syncthreads();
+      const long long tb1 = pclock();
+      panel_solve<ld>(dt_off, c0, rd_off + c0);
+      __syncthreads();
+      const long long tb2 = pclock();
+      if (RACG_PHASE_TIMERS && threadIdx.x == 0) ph[PH_B_PANEL] += tb2 - tb1;
+      const double* const Lb = Dt + c0 * ld + ti;      // L21(ti + 16 a, k) = Lb[k * ld + 16 a]
+      const double* const Ub = Dt + tj * ld + c0;      // U12(k, tj + 16 b) = Ub[16 b * ld + k]
+#pragma unroll 4
+      for (int k = 0; k < 16; ++k) {
+        double lr[TL], uc[TL];
+#pragma unroll
+        for (int a = p + 1; a < TL; ++a) lr[a] = Lb[k * ld + 16 * a];
+#pragma unroll
+        for (int b = p + 1; b < TL; ++b) uc[b] = Ub[16 * b * ld + k];
+#pragma unroll
+        for (int a = p + 1; a < TL; ++a)
+#pragma unroll
+          for (int b = p + 1; b < TL; ++b) t[a][b] -= lr[a] * uc[b];
+      }
+      // the next panel's column slice and row slice go back to shared memory; the rest stays in registers
+#pragma unroll
+      for (int a = p + 1; a < TL; ++a) Dt[(tj + 16 * (p + 1)) * ld + ti + 16 * a] = t[a][p + 1];
+#pragma unroll
+      for (int b = p + 2; b < TL; ++b) Dt[(tj + 16 * b) * ld + ti + 16 * (p + 1)] = t[p + 1][b];
+      __syncthreads();
+      if (RACG_PHASE_TIMERS && threadIdx.x == 0) ph[PH_B_UPD] += pclock() - tb2;
+    }
+  }
+  __syncthreads();
+}
+
+template <int TL>
+__device__ __noinline__ void tail_lu(int dt_off, int pub_off, int* flag, unsigned long long* ph) {   // reciprocal pivots -> dinv[nh + k]
+  if constexpr (TJ == 16) { tail_lu_blocked<TL>(dt_off, pub_off, flag, ph); return; }
   const DevNet& net = c_net;
   constexpr int TC = (16 * TL + TJ - 1) / TJ;
   const int nt = net.nt, ldt = net.ldt;
@@ -496,15 +640,24 @@ __device__ __noinline__ void warp_trisolve_upper(int t_off, int ld, int nt, int 
       double a[WIN][8], u10[4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        a[0][j] = (l < c0 + j) ? col[j * ld] * rdl : 0.0;
+        a[0][j] = (base + l < nt) ? col[j * ld] : 0.0;
 #pragma unroll
         for (int m = 1; m < WIN; ++m) a[m][j] = (mb >= m) ? col[j * ld - 32 * m] : 0.0;
       }
       // pairs of columns (c, c-1) as in the forward sweep: x_{c-1} = s_{c-1} - (U(c-1,c) rd_{c-1}) x_c
+      double r10[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        u10[q] = T[(base + c0 + 2 * q + 1) * ld + base + c0 + 2 * q] * rd[base + c0 + 2 * q];
+      for (int q = 0; q < 4; ++q) {
+        u10[q] = T[(base + c0 + 2 * q + 1) * ld + base + c0 + 2 * q];
+        r10[q] = rd[base + c0 + 2 * q];
+      }
       col -= 8 * ld;
+      // all loads first, then the scaling: a multiply issued right behind its load would stall
+      // the only running warp for the full shared-memory latency, eight times per group
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[0][j] = (l < c0 + j) ? a[0][j] * rdl : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u10[q] *= r10[q];
 #pragma unroll
       for (int q = 3; q >= 0; --q) {
         const double xc = __shfl_sync(0xffffffffu, x[0], c0 + 2 * q + 1);
@@ -518,6 +671,162 @@ __device__ __noinline__ void warp_trisolve_upper(int t_off, int ld, int nt, int 
 #pragma unroll
     for (int m = 0; m + 1 < WIN; ++m) x[m] = x[m + 1];
     x[WIN - 1] = 0.0;
+  }
+}
+
+// Dense-tail substitution (L x = b, then U x = y; nt <= 128) by up to four warps, tid < 128.
+// Warp w owns the 32-row block w of the right-hand side, one row per lane, in a register.  A
+// sweep visits the diagonal blocks in order; the owner of the current one runs the column-pair
+// chain of warp_trisolve_* on it and publishes every finished group of 8 unknowns to xs[]
+// followed by a progress counter; the owners of the blocks still to come wait on that counter
+// and subtract the group's columns from their rows right away, operands fetched before the wait.
+// When a chain ends the next owner is a few FMAs behind, so the critical path is the diagonal
+// chains alone -- the off-diagonal updates, which used to share the chain warp's issue slots,
+// run beside it.  Every row sees the same operations in the same order as in the single-warp
+// sweep: results are bit-identical.  ctr: two ints, zeroed by the caller before a barrier
+// (forward progress = columns done from the left, backward = from the right).
+// Ordering of the hand-off: the unknowns and the counter are stored by the same warp to shared
+// memory in program order with a __syncwarp() between (lanes c0..c0+7, then lane 0), and read by
+// the consumer counter first, data (volatile) after the branch that depends on it;
+// RACG_TAIL_FENCE=1 makes both sides explicit release / acquire operations (measured: no
+// difference in time, identical results).
+// (A variant that broadcast four unknowns at a time through shared memory instead of shuffling
+// pairs was bit-identical and not faster: the chains run ~4 groups per call and their time is
+// dominated by the cold start of each code path, see DESIGN.md.)
+#ifndef RACG_TAIL_FENCE
+#define RACG_TAIL_FENCE 0
+#endif
+__device__ __forceinline__ void st_release_smem(int* p, int v) {
+#if RACG_TAIL_FENCE
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#else
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ int ld_acquire_smem(const int* p) {
+  int v;
+#if RACG_TAIL_FENCE
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+#else
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+#endif
+  return v;
+}
+__device__ __noinline__ void tail_trisolve_mw(int t_off, int ld, int nt, int rd_off, int xs_off, int ctr_off, unsigned long long* ph) {
+  const double* const T = smem_raw + t_off;
+  const double* const rd = smem_raw + rd_off;
+  double* const xs = smem_raw + xs_off;
+  int* const ctrL = (int*)(smem_raw + ctr_off);
+  int* const ctrU = ctrL + 1;
+  const int l = threadIdx.x & 31, w = threadIdx.x >> 5, nb = (nt + 31) >> 5;
+  if (w >= nb) return;
+  const int base = 32 * w, cmax = (nt - base) < 32 ? (nt - base) : 32;
+  const bool on = l < cmax;
+  double x = on ? xs[base + l] : 0.0;
+  const long long tp0 = pclock();
+  // ---------------- forward
+#pragma unroll 1
+  for (int cb = 0; cb < w; ++cb) {
+    const double* col = T + (32 * cb) * ld + base + l;
+    const volatile double* xv = xs + 32 * cb;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+      double a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = on ? col[j * ld] : 0.0;
+      col += 8 * ld;
+      const int need = 32 * cb + c0 + 8;
+      while (ld_acquire_smem(ctrL) < need) {}
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = xv[c0 + j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x -= a[j] * v[j];
+    }
+  }
+  {
+    const double* col = T + base * ld + base + l;
+#pragma unroll 1
+    for (int c0 = 0; c0 < cmax; c0 += 8) {
+      double a[8], l10[4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = (on && l > c0 + j) ? col[j * ld] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) l10[q] = T[(base + c0 + 2 * q) * ld + base + c0 + 2 * q + 1];
+      col += 8 * ld;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double xc = __shfl_sync(0xffffffffu, x, c0 + 2 * q);
+        const double x1p = __shfl_sync(0xffffffffu, x, c0 + 2 * q + 1);
+        const double x1f = x1p - l10[q] * xc;
+        x -= a[2 * q] * xc;
+        x -= a[2 * q + 1] * x1f;
+      }
+      if (l >= c0 && l < c0 + 8) xs[base + l] = x;
+      __syncwarp();
+      if (l == 0) st_release_smem(ctrL, base + c0 + 8);
+    }
+  }
+  const long long tp1 = pclock();
+  // ---------------- backward (x = this block's forward result)
+#pragma unroll 1
+  for (int cb = nb - 1; cb > w; --cb) {
+    const int cbm = (nt - 32 * cb) < 32 ? (nt - 32 * cb) : 32;
+    const double* col = T + (32 * cb + cbm - 8) * ld + base + l;
+    const volatile double* xv = xs + 32 * cb;
+#pragma unroll 1
+    for (int c0 = cbm - 8; c0 >= 0; c0 -= 8) {
+      double a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = col[j * ld];
+      col -= 8 * ld;
+      const int need = nt - (32 * cb + c0);
+      while (ld_acquire_smem(ctrU) < need) {}
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = xv[c0 + j];
+#pragma unroll
+      for (int j = 7; j >= 0; --j) x -= a[j] * v[j];
+    }
+  }
+  const long long tp2 = pclock();
+  {
+    // the block is carried scaled by its reciprocal pivots (see warp_trisolve_upper)
+    const double rdl = on ? rd[base + l] : 1.0;
+    x *= rdl;
+    const double* col = T + (base + cmax - 8) * ld + base + l;
+#pragma unroll 1
+    for (int c0 = cmax - 8; c0 >= 0; c0 -= 8) {
+      double a[8], u10[4], r10[4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = on ? col[j * ld] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        u10[q] = T[(base + c0 + 2 * q + 1) * ld + base + c0 + 2 * q];
+        r10[q] = rd[base + c0 + 2 * q];
+      }
+      col -= 8 * ld;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = (l < c0 + j) ? a[j] * rdl : 0.0;   // loads first, scaling after
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u10[q] *= r10[q];
+#pragma unroll
+      for (int q = 3; q >= 0; --q) {
+        const double xc = __shfl_sync(0xffffffffu, x, c0 + 2 * q + 1);
+        const double x1p = __shfl_sync(0xffffffffu, x, c0 + 2 * q);
+        const double x1f = x1p - u10[q] * xc;
+        x -= a[2 * q + 1] * xc;
+        x -= a[2 * q] * x1f;
+      }
+      if (l >= c0 && l < c0 + 8) xs[base + l] = x;
+      __syncwarp();
+      if (l == 0) st_release_smem(ctrU, nt - (base + c0));
+    }
+  }
+  if (RACG_PHASE_TIMERS && l == 0 && ph != nullptr) {
+    const long long tp3 = pclock();
+    if (w == 0) { ph[PH_T_L0] += tp1 - tp0; ph[PH_T_W0MID] += tp2 - tp1; ph[PH_T_U0] += tp3 - tp2; }
+    if (w == nb - 1 && w > 0) { ph[PH_T_LALL] += tp1 - tp0; ph[PH_T_UTOP] += tp3 - tp2; }
   }
 }
 
@@ -763,10 +1072,10 @@ __device__ __noinline__ int factor_glu(Ws ws, double con, int* flag, unsigned lo
   // ---- dense tail
   const int dto = (int)(sm.Dt - smem_raw), pbo = (int)(sm.X - smem_raw);
   switch (nt >> 4) {
-    case 1: tail_lu<1>(dto, pbo, flag); break; case 2: tail_lu<2>(dto, pbo, flag); break;
-    case 3: tail_lu<3>(dto, pbo, flag); break; case 4: tail_lu<4>(dto, pbo, flag); break;
-    case 5: tail_lu<5>(dto, pbo, flag); break; case 6: tail_lu<6>(dto, pbo, flag); break;
-    case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
+    case 1: tail_lu<1>(dto, pbo, flag, ph); break; case 2: tail_lu<2>(dto, pbo, flag, ph); break;
+    case 3: tail_lu<3>(dto, pbo, flag, ph); break; case 4: tail_lu<4>(dto, pbo, flag, ph); break;
+    case 5: tail_lu<5>(dto, pbo, flag, ph); break; case 6: tail_lu<6>(dto, pbo, flag, ph); break;
+    case 7: tail_lu<7>(dto, pbo, flag, ph); break; default: tail_lu<8>(dto, pbo, flag, ph); break;
   }
   const long long t2b = pclock();
   const int res = *flag;
@@ -895,10 +1204,10 @@ __device__ __forceinline__ int factor(Ws ws, Smem sm, Layout lay, double con, in
   // ---- dense tail
   const int dto = (int)(sm.Dt - smem_raw), pbo = (int)(sm.X - smem_raw);
   switch (nt >> 4) {
-    case 1: tail_lu<1>(dto, pbo, flag); break; case 2: tail_lu<2>(dto, pbo, flag); break;
-    case 3: tail_lu<3>(dto, pbo, flag); break; case 4: tail_lu<4>(dto, pbo, flag); break;
-    case 5: tail_lu<5>(dto, pbo, flag); break; case 6: tail_lu<6>(dto, pbo, flag); break;
-    case 7: tail_lu<7>(dto, pbo, flag); break; default: tail_lu<8>(dto, pbo, flag); break;
+    case 1: tail_lu<1>(dto, pbo, flag, ph); break; case 2: tail_lu<2>(dto, pbo, flag, ph); break;
+    case 3: tail_lu<3>(dto, pbo, flag, ph); break; case 4: tail_lu<4>(dto, pbo, flag, ph); break;
+    case 5: tail_lu<5>(dto, pbo, flag, ph); break; case 6: tail_lu<6>(dto, pbo, flag, ph); break;
+    case 7: tail_lu<7>(dto, pbo, flag, ph); break; default: tail_lu<8>(dto, pbo, flag, ph); break;
   }
   long long t2b = pclock();
   const int res = *flag;
@@ -1059,6 +1368,7 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
   EllRegs<U> R;
   ell_fetch(net.lcE, ws.lcE, R);           // lands while the head sweep runs
   for (int i = tid; i < n; i += NT) sm.xb[i] = sm.y[__ldg(net.perm + i)];
+  if (tid == 0) *(long long*)(smem_raw + 3 * n + 32) = 0;     // progress counters of the tail sweeps
   __syncthreads();
   for (int st = 0; st < net.ss.nf; ++st) head_stage(sm.st[st], sm, ent, rp, rows, tmp, false);
   const long long t1 = pclock();
@@ -1067,11 +1377,8 @@ __device__ __noinline__ void solve_glu(Ws ws, unsigned long long* ph) {
   ell_fetch(net.ubE, ws.ubE, R);           // lands while the tail is solved
   const long long t1b = pclock();
   // ---- dense tail: forward and backward substitution on warp 0
-  if (tid < 32) {
-    const int dto = (int)(sm.Dt - smem_raw), xo = (int)(sm.xb - smem_raw) + nh;
-    warp_trisolve_lower<4>(dto, ldt, nt, xo);
-    warp_trisolve_upper<4>(dto, ldt, nt, (int)(sm.dinv - smem_raw) + nh, xo);
-  }
+  if (tid < 128)
+    tail_trisolve_mw((int)(sm.Dt - smem_raw), ldt, nt, (int)(sm.dinv - smem_raw) + nh, (int)(sm.xb - smem_raw) + nh, 3 * n + 32, ph);
   __syncthreads();
   const long long t1c = pclock();
   // ---- head right-hand side: x_H -= U_B x_T
@@ -1099,6 +1406,7 @@ __device__ __forceinline__ void solve(Ws ws, Smem sm, bool wiped, double pw) {
     return;
   }
   for (int i = tid; i < n; i += NT) sm.xb[i] = sm.y[net.perm[i]];
+  if (tid == 0) *(long long*)(smem_raw + 3 * n + 32) = 0;     // progress counters of the tail sweeps
   __syncthreads();
   // ---- forward, head: fat levels by the CTA, thin levels (<= 32 rows) by warp 0
   for (int lev = 1; lev < net.nfat_f; ++lev) {
@@ -1128,11 +1436,8 @@ __device__ __forceinline__ void solve(Ws ws, Smem sm, bool wiped, double pw) {
   // ---- tail right-hand side: x_T -= L_C x_H
   spmv_sub(net.lcE, ws.lcE, sm.xb, sm.xb + nh, sm.X);
   // ---- dense tail: forward and backward substitution on warp 0
-  if (w == 0) {
-    const int dto = (int)(sm.Dt - smem_raw), xo = (int)(sm.xb - smem_raw) + nh;
-    warp_trisolve_lower<4>(dto, ldt, nt, xo);
-    warp_trisolve_upper<4>(dto, ldt, nt, (int)(sm.dinv - smem_raw) + nh, xo);
-  }
+  if (tid < 128)
+    tail_trisolve_mw((int)(sm.Dt - smem_raw), ldt, nt, (int)(sm.dinv - smem_raw) + nh, (int)(sm.xb - smem_raw) + nh, 3 * n + 32, nullptr);
   __syncthreads();
   // ---- head right-hand side: x_H -= U_B x_T
   spmv_sub(net.ubE, ws.ubE, sm.xb + nh, sm.xb, sm.X);
@@ -2016,7 +2321,7 @@ static DevSerial g_serial[64];
 
 cudaError_t launch_integrate(const DevNet& net, unsigned long long net_id, int device, const BatchArgs& args,
                              int nblocks, size_t smem, cudaStream_t stream) {
-  if (net.nt > 16 * MAXTL || (net.nt & 15) || device < 0 || device >= 64) return cudaErrorInvalidValue;
+  if (net.nt > 16 * MAXTL || (net.nt & 15) || net.ldt != net.nt + 1 || device < 0 || device >= 64) return cudaErrorInvalidValue;
   DevSerial& S = g_serial[device];
   std::lock_guard<std::mutex> lk(S.mu);
   cudaError_t e;

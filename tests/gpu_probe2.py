@@ -33,6 +33,10 @@ print("per LU: total %.0f pbuild %.0f glu_loop %.0f (pivmul %.0f flat %.0f narro
 print("per solve: total %.0f fwd %.0f tail %.0f bwd %.0f spmv %.0f | per f: %.0f (flux %.0f gather %.0f) | jac %.0f | vec/step %.0f" % (
     ph["solve"]/nsolve, ph["solve_fwd"]/nsolve, ph["solve_tail"]/nsolve, ph["solve_bwd"]/nsolve, ph["solve_spmv"]/nsolve,
     ph["f"]/nfe, ph["f_flux"]/nfe, ph["f_gather"]/nfe, ph["jac"]/max(nje,1), ph["vec"]/nst))
+print("tail sweeps per solve: warp0 L chain %.0f | last warp until its L chain ends %.0f | warp0 between its chains %.0f | warp0 U chain %.0f | top U chain %.0f" % (
+    ph["tail_L0"]/nsolve, ph["tail_Lall"]/nsolve, ph["tail_w0mid"]/nsolve, ph["tail_U0"]/nsolve, ph["tail_Utop"]/nsolve))
+print("blocked tail LU per factorisation: diagonal blocks %.0f | panel solves %.0f | trailing updates %.0f" % (
+    ph["blk_diag"]/nlu, ph["blk_panel"]/nlu, ph["blk_update"]/nlu))
 if ncheck:
     import raco
     onet = raco.Network(os.path.join(inp, netname))
