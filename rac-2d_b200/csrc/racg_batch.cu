@@ -498,6 +498,209 @@ jac_kernel_wide(const DevNet net, const JacColTables jc, int ncell, const double
   }
 }
 
+// K3, pipelined variant (the default when ncell is a multiple of 4, or even): same column groups
+// as jac_kernel_wide, a lane owns CPL consecutive cells and a CTA of NTH threads a tile of 32*CPL
+// cells, two CTAs per SM; but no dependent index chains and no register-staged rate loads:
+//   * phase 1a: the rate rows of ALL pairs of the group are requested at once with cp.async
+//     (16-byte pieces straight into the pair's row of the derivative buffer), so a whole group
+//     (<= 96 rows x 1 KB) is in flight per CTA instead of two rows per warp;
+//   * phase 1b: the pair words (flux word + reaction, one 8-byte load: HostNet::JacCols::pairw) are
+//     read again (L1 hits), the abundances fetched PB pairs at a time, and the derivative
+//     overwrites the rate in place;
+//   * phase 2: listed slots heaviest first, their words (slotw: CSC slot, entry offset, count) two
+//     slots ahead, the first entry group and -- for the chunks of a hub column -- the value an
+//     earlier chunk stored one slot ahead; entries in groups of four (uint4), padded with +1 x a
+//     zero row; an entry carries the high 16 bits of its coefficient as a double (no int->double
+//     conversion in the loop).
+// CPL = 4 halves the per-pair / per-slot / per-entry instruction overhead per cell against CPL = 2
+// (measured with ncu: the CPL = 2 form issues 3.0 G warp-instructions for 75 776 cells and is
+// issue-bound at 36 % of the HBM peak).  The group pointers sit in shared memory behind the buffer.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int CPL>
+__device__ __forceinline__ DV<CPL> ldv_g(const double* p) {
+  DV<CPL> r;
+#pragma unroll
+  for (int q = 0; q < CPL; q += 2) { const double2 a = __ldg((const double2*)p + (q >> 1)); r.v[q] = a.x; r.v[q + 1] = a.y; }
+  return r;
+}
+template <int CPL>
+__device__ __forceinline__ DV<CPL> ldv_s(const double* p) {
+  DV<CPL> r;
+#pragma unroll
+  for (int q = 0; q < CPL; q += 2) { const double2 a = *((const double2*)p + (q >> 1)); r.v[q] = a.x; r.v[q + 1] = a.y; }
+  return r;
+}
+
+template <int CPL, int NTH, int PB>
+__global__ void __launch_bounds__(NTH, 1024 / NTH)
+jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double* __restrict__ cellpar,
+                const double* __restrict__ y, const double* __restrict__ rates, double* __restrict__ pd) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int TC = 32 * CPL, NWARP = NTH >> 5;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double* const dbuf = sm;                                   // [max_pairs + 1][TC], the last row = 0
+  int* const gp = (int*)(dbuf + (size_t)(jc.max_pairs + 1) * TC);   // pair_ptr[ng+1] | slot_ptr[ng+1] | accum[ng]
+  const int ng = jc.ngroups;
+  int* const gs = gp + ng + 1;
+  int* const ga = gs + ng + 1;
+  int* const g2 = ga + ng;            // first two-body pair
+  int* const g3 = g2 + ng;            // first saturating pair
+  for (int i = threadIdx.x; i <= ng; i += NTH) { gp[i] = __ldg(jc.grp_pair_ptr + i); gs[i] = __ldg(jc.grp_slot_ptr + i); }
+  for (int i = threadIdx.x; i < ng; i += NTH) { ga[i] = __ldg(jc.grp_accum + i); g2[i] = __ldg(jc.grp_two_ptr + i); g3[i] = __ldg(jc.grp_sat_ptr + i); }
+  const unsigned ncu = (unsigned)ncell;
+  for (int i = threadIdx.x; i < TC; i += NTH) dbuf[(size_t)jc.max_pairs * TC + i] = 0.0;
+  const uint2* const pairw = (const uint2*)jc.pairw;
+  const uint2* const slotw = (const uint2*)jc.slotw;
+  const uint4* const ent4 = (const uint4*)jc.ent4;
+  double* const myd = dbuf + CPL * l;                        // this lane's columns of the buffer
+  const double2 z2 = make_double2(0.0, 0.0);
+  for (int tile = blockIdx.x; tile * TC < ncell; tile += gridDim.x) {
+    const int cell = tile * TC + CPL * l;
+    const bool ok = cell < ncell;                            // ncell % CPL == 0: all cells of a lane or none
+    const double* const yc = y + (ok ? cell : 0);
+    double* const pdc = pd + (ok ? cell : 0);
+    double DS[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) DS[q] = 1.0;
+    if (ok) {
+      const DV<CPL> a1 = ldv_g<CPL>(cellpar + (size_t)RACG_P_ratioDust2HnucNum * ncell + cell);
+      const DV<CPL> a2 = ldv_g<CPL>(cellpar + (size_t)RACG_P_SitesPerGrain * ncell + cell);
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) DS[q] = a1.v[q] * a2.v[q];
+      for (int z = w; z < jc.nzero; z += NWARP) {
+        double2* const o = (double2*)(pd + (size_t)__ldg(jc.zero_slots + z) * ncell + cell);
+#pragma unroll
+        for (int q = 0; q < CPL / 2; ++q) __stcs(o + q, z2);
+      }
+    }
+    for (int g = 0; g < ng; ++g) {
+      __syncthreads();                                       // the previous group's gather is done with dbuf (and gp[] is set)
+      const int pb = gp[g], pe = gp[g + 1];
+      // ---- 1a: every rate row of the group
+      if (ok) {
+        const double* const rc = rates + cell;
+#pragma unroll 4
+        for (int p = pb + w; p < pe; p += NWARP) {
+          const double* const src = rc + (size_t)((unsigned long long)__ldg(&pairw[p].y) * ncu);
+          double* const dst = myd + (p - pb) * TC;
+#pragma unroll
+          for (int q = 0; q < CPL; q += 2) cp_async16(dst + q, src + q);
+        }
+      }
+      // ---- 1b: derivatives in place (branches of chem_ode_jac, src/disk.f90:4765-4866).  One-body
+      // pairs: the derivative is the rate, nothing to do.  Two-body pairs, PB at a time:
+      bool landed = false;
+      const int p2 = g2[g], p3 = g3[g];
+      // (a pair is finished by the warp that requested its rate row: p = pb + w modulo NWARP, so that
+      // the warp's own cp.async wait covers it)
+      for (int p0 = p2 + ((w - (p2 - pb)) & (NWARP - 1)); p0 < p3; p0 += PB * NWARP) {
+        uint32_t xw[PB]; DV<CPL> yo[PB], ys[PB];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+          const int p = p0 + u * NWARP;
+          xw[u] = (p < p3) ? __ldg(&pairw[p].x) : 0u;
+          yo[u] = ldv_g<CPL>(yc + (size_t)((unsigned long long)(xw[u] & 1023u) * ncu));
+          ys[u] = ldv_g<CPL>(yc + (size_t)((unsigned long long)((xw[u] >> 10) & 1023u) * ncu));
+        }
+        if (!landed) { cp_async_wait_all(); landed = true; }
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+          const int p = p0 + u * NWARP;
+          if (p < p3) {
+            double* const kp = myd + (p - pb) * TC;
+            const DV<CPL> k = ldv_s<CPL>(kp);
+            const double fac = (xw[u] >> 20) ? 2.0 : 1.0;
+            double d[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+              const double dd = fac * k.v[q] * yo[u].v[q];
+              d[q] = (yo[u].v[q] < 0.0 && ys[u].v[q] < 0.0) ? -dd : dd;
+            }
+#pragma unroll
+            for (int q = 0; q < CPL; q += 2) *((double2*)kp + (q >> 1)) = make_double2(d[q], d[q + 1]);
+          }
+        }
+      }
+      // saturating desorption (a handful per network)
+      for (int p = p3 + ((w - (p3 - pb)) & (NWARP - 1)); p < pe; p += NWARP) {
+        const uint32_t x = __ldg(&pairw[p].x);
+        const DV<CPL> y1 = ldv_g<CPL>(yc + (size_t)((unsigned long long)(x & 1023u) * ncu));
+        if (!landed) { cp_async_wait_all(); landed = true; }
+        double* const kp = myd + (p - pb) * TC;
+        const DV<CPL> k = ldv_s<CPL>(kp);
+        const double sc = net.sat_c[x >> 10];
+        double d[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          double dd = 0.0;
+          const double tmp2 = DS[q] * sc;
+          if (tmp2 > 0.0) {
+            const double tmp1 = 1.0 / tmp2, tmp = y1.v[q] * tmp1;
+            dd = (tmp <= 1e-4) ? k.v[q] * tmp1 : k.v[q] * tmp1 * exp(-tmp);
+          }
+          d[q] = dd;
+        }
+#pragma unroll
+        for (int q = 0; q < CPL; q += 2) *((double2*)kp + (q >> 1)) = make_double2(d[q], d[q + 1]);
+      }
+      if (!landed) cp_async_wait_all();
+      __syncthreads();
+      // ---- 2: gather the listed slots
+      const int se = gs[g + 1];
+      const bool accum = ga[g] != 0 && ok;
+      int s = gs[g] + w;
+      const uint2 none = make_uint2(0u, 0u);
+      uint2 c0 = (s < se) ? __ldg(slotw + s) : none;
+      uint2 c1 = (s + NWARP < se) ? __ldg(slotw + s + NWARP) : none;
+      uint4 e0 = __ldg(ent4 + (c0.y & 0xffffffu));
+      // coherent reads (not the read-only path): an earlier group of this kernel stored the value
+      double a0[CPL];
+#pragma unroll
+      for (int q = 0; q < CPL; q += 2) {
+        const double2 t = accum ? __ldcg((const double2*)(pdc + (size_t)((unsigned long long)c0.x * ncu)) + (q >> 1)) : z2;
+        a0[q] = t.x; a0[q + 1] = t.y;
+      }
+      for (; s < se; s += NWARP) {
+        const uint2 c2 = (s + 2 * NWARP < se) ? __ldg(slotw + s + 2 * NWARP) : none;
+        const uint4 e1 = __ldg(ent4 + (c1.y & 0xffffffu));
+        double a1[CPL];
+        const bool more = accum && s + NWARP < se;
+#pragma unroll
+        for (int q = 0; q < CPL; q += 2) {
+          const double2 t = more ? __ldcg((const double2*)(pdc + (size_t)((unsigned long long)c1.x * ncu)) + (q >> 1)) : z2;
+          a1[q] = t.x; a1[q + 1] = t.y;
+        }
+        const int n4 = (int)(c0.y >> 24);
+        const uint4* const ep = ent4 + (c0.y & 0xffffffu);
+        uint4 e = e0;
+        for (int i4 = 0;;) {
+          const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const DV<CPL> dv = ldv_s<CPL>(myd + (ev[j] & 0xffffu) * TC);
+            const double cf = __hiloint2double((int)(ev[j] & 0xffff0000u), 0);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) a0[q] += cf * dv.v[q];
+          }
+          if (++i4 >= n4) break;
+          e = __ldg(ep + i4);
+        }
+        if (ok) {
+          double2* const o = (double2*)(pdc + (size_t)((unsigned long long)c0.x * ncu));
+#pragma unroll
+          for (int q = 0; q < CPL; q += 2) __stcs(o + (q >> 1), make_double2(a0[q], a0[q + 1]));
+        }
+        c0 = c1; c1 = c2; e0 = e1;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) a0[q] = a1[q];
+      }
+    }
+  }
+}
+
 cudaError_t launch_rates(const DevNet& net, int ncell, const double* cellpar, double* rates, cudaStream_t st) {
   rates_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(net, ncell, cellpar, rates);
   return cudaGetLastError();
@@ -566,12 +769,22 @@ cudaError_t launch_rhs(const DevNet& net, const RhsChunkDev& rc, int ncell, cons
   return cudaGetLastError();
 }
 
-int g_k3_variant = 2;   // 2: two 64-cell CTAs per SM (default), 4: one 128-cell CTA per SM (A/B measurements)
+int g_k3_variant = 3;   // 3: jac_kernel_pipe (default); 2: jac_kernel_wide<2,512>; 4: jac_kernel_wide<4,1024> (A/B measurements)
 cudaError_t launch_jac(const DevNet& net, const JacColTables& jc, int ncell, const double* cellpar, const double* y,
                        const double* rates, double* pd, int nsm, cudaStream_t st) {
   const bool aligned = ((size_t)pd % 32) == 0 && ((size_t)y % 32) == 0 && ((size_t)rates % 32) == 0 && ((size_t)cellpar % 32) == 0;
   // two 64-cell CTAs per SM (lane = 2 cells) when their derivative buffers fit side by side
   const size_t smem2 = (size_t)jc.max_pairs * 64 * sizeof(double);
+  // pipelined kernel: two CTAs per SM, 64-cell tiles (lane = 2 cells)
+  const size_t smemp = ((size_t)jc.max_pairs + 1) * 64 * sizeof(double) + (5 * (size_t)jc.ngroups + 2) * sizeof(int);
+  if (g_k3_variant == 3 && ncell % 2 == 0 && aligned && (smemp + 1024) * 2 <= 227 * 1024) {
+    auto kern = jac_kernel_pipe<2, 512, 4>;
+    cudaError_t e3 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp);
+    if (e3 != cudaSuccess) return e3;
+    const int ntiles = (ncell + 63) / 64;
+    kern<<<ntiles < 2 * nsm ? ntiles : 2 * nsm, 512, smemp, st>>>(net, jc, ncell, cellpar, y, rates, pd);
+    return cudaGetLastError();
+  }
   if (g_k3_variant != 4 && ncell % 2 == 0 && aligned && (smem2 + 1024) * 2 <= 227 * 1024) {
     auto kern = jac_kernel_wide<2, 512>;
     cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);

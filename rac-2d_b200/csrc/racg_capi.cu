@@ -284,6 +284,11 @@ static int create_ctx(racg_handle* h, int device, DevCtx** out) {
     if ((rc = upload(c, s.slot_ent_ptr, &jc.slot_ent_ptr))) return rc;
     if ((rc = upload(c, s.ent, &jc.ent))) return rc;
     if ((rc = upload(c, s.zero_slots, &jc.zero_slots))) return rc;
+    if ((rc = upload(c, s.pairw, &jc.pairw))) return rc;
+    if ((rc = upload(c, s.slotw, &jc.slotw))) return rc;
+    if ((rc = upload(c, s.ent4, &jc.ent4))) return rc;
+    if ((rc = upload(c, s.grp_two_ptr, &jc.grp_two_ptr))) return rc;
+    if ((rc = upload(c, s.grp_sat_ptr, &jc.grp_sat_ptr))) return rc;
   }
 #undef UP
   if ((rc = finish_ctx(h, c))) return rc;

@@ -143,6 +143,9 @@ struct JacColTables {
   const uint32_t* ent;        // local pair index | (coef+4)<<24
   int max_pairs;
   int nzero; const int* zero_slots;   // CSC slots that are structurally zero for evolT=F (T row/col etc.)
+  // repacked copies for jac_kernel_pipe (HostNet::JacCols::pairw / slotw / ent4)
+  const uint32_t* pairw; const uint32_t* slotw; const uint32_t* ent4;
+  const int* grp_two_ptr; const int* grp_sat_ptr;
 };
 
 }  // namespace racg

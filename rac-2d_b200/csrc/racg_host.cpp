@@ -772,7 +772,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
   // derivatives fit the shared-memory buffer; hub columns are cut into chunks that
   // accumulate into pd.
   {
-    const int CAP = 192;
+    const int CAP = 192;     // pairs per group: 192 rows x 512 B (64-cell tiles) fit twice in an SM's shared memory
     HostNet::JacCols& jc = hn.jc;
     std::vector<std::vector<uint32_t>> col_pairs(NEQ);
     for (int i = 0; i < R; ++i) {
@@ -796,6 +796,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     auto emit_group = [&](const std::vector<std::pair<int, std::pair<int, int>>>& colranges, int accum) {
       // colranges: (column j, (first pair, last pair))
       int local = 0;
+      const size_t pair0 = jc.pair.size(), ent0 = jc.ent.size();
       for (auto& cr : colranges) {
         int j = cr.first;
         for (int k = hn.ia[j] - 1; k < hn.ia[j + 1] - 1; ++k) slot_of_row[hn.ja[k] - 1] = k;
@@ -816,6 +817,24 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
           jc.slot_ent_ptr.push_back((int)jc.ent.size());
           if (!accum) written[ps.first] = 1;
         }
+      }
+      // pairs of a group ordered by flux kind (one-body | two-body | saturating): branch-free loops
+      // in jac_kernel_pipe, nothing to do for the one-body pairs (the derivative is the rate)
+      {
+        auto rank = [&](uint32_t pr) { const int kind = (hn.fw[pr & 0xffff] >> 20) & 3; return kind == FK_ONE ? 0 : kind == FK_TWO ? 1 : 2; };
+        std::vector<int> perm(local), inv(local);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return rank(jc.pair[pair0 + a]) < rank(jc.pair[pair0 + b]); });
+        std::vector<uint32_t> old(jc.pair.begin() + pair0, jc.pair.end());
+        int n1 = 0, n2 = 0;
+        for (int q = 0; q < local; ++q) {
+          jc.pair[pair0 + q] = old[perm[q]]; inv[perm[q]] = q;
+          const int rk = rank(old[perm[q]]);
+          n1 += rk == 0; n2 += rk <= 1;
+        }
+        for (size_t e = ent0; e < jc.ent.size(); ++e) jc.ent[e] = (jc.ent[e] & 0xff000000u) | (uint32_t)inv[jc.ent[e] & 0xffffffu];
+        jc.grp_two_ptr.push_back((int)pair0 + n1);
+        jc.grp_sat_ptr.push_back((int)pair0 + n2);
       }
       jc.grp_pair_ptr.push_back((int)jc.pair.size());
       jc.grp_slot_ptr.push_back((int)jc.slot_id.size());
@@ -839,6 +858,35 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
     if (!cur.empty()) emit_group(cur, 0);
     jc.ngroups = (int)jc.grp_accum.size();
     for (int k = 0; k < hn.NNZ; ++k) if (!written[k]) jc.zero_slots.push_back(k);
+    // repack for jac_kernel_pipe
+    // pair word x: two-body -> row of the other reactant | row of this column's reactant << 10 | (r1 == r2) << 20;
+    //              saturating -> r1 | saturation constant index << 10;  y: reaction (rate row)
+    for (uint32_t pr : jc.pair) {
+      const uint32_t w = hn.fw[pr & 0xffff];
+      const int kind = (w >> 20) & 3, which = pr >> 16;
+      const uint32_t r1 = w & 1023, r2 = (w >> 10) & 1023;
+      uint32_t x = 0;
+      if (kind == FK_TWO) x = (which == 0 ? r2 : r1) | ((which == 0 ? r1 : r2) << 10) | ((r1 == r2 ? 1u : 0u) << 20);
+      else if (kind == FK_SAT) x = r1 | ((w >> 22) << 10);
+      jc.pairw.push_back(x); jc.pairw.push_back(pr & 0xffff);
+    }
+    // entry of the repacked lists: local pair index | high 16 bits of the coefficient as a double
+    auto cf16 = [](int c) { const double d = (double)c; uint64_t b; memcpy(&b, &d, 8); return (uint32_t)(b >> 48) << 16; };
+    const uint32_t padent = (uint32_t)jc.max_pairs | cf16(1);
+    for (int g = 0; g < jc.ngroups; ++g) {
+      std::vector<std::pair<int, int>> ord;   // (-entries, listed slot)
+      for (int s2 = jc.grp_slot_ptr[g]; s2 < jc.grp_slot_ptr[g + 1]; ++s2)
+        ord.push_back({-(jc.slot_ent_ptr[s2 + 1] - jc.slot_ent_ptr[s2]), s2});
+      std::sort(ord.begin(), ord.end());
+      for (auto& o : ord) {
+        const int s2 = o.second, e0 = jc.slot_ent_ptr[s2], e1 = jc.slot_ent_ptr[s2 + 1];
+        const int n4 = (e1 - e0 + 3) / 4;
+        jc.slotw.push_back((uint32_t)jc.slot_id[s2]);
+        jc.slotw.push_back((uint32_t)(jc.ent4.size() / 4) | ((uint32_t)n4 << 24));
+        for (int e = e0; e < e0 + 4 * n4; ++e)
+          jc.ent4.push_back(e < e1 ? ((jc.ent[e] & 0xffffu) | cf16((int)(jc.ent[e] >> 24) - 4)) : padent);
+      }
+    }
   }
   return true;
 }

@@ -170,6 +170,11 @@ struct HostNet {
     std::vector<int> slot_id, slot_ent_ptr;
     std::vector<uint32_t> ent;         // local pair idx | (coef+4)<<24
     std::vector<int> zero_slots;
+    // the same schedule repacked for jac_kernel_pipe (one load per item, no dependent index chains):
+    std::vector<int> grp_two_ptr, grp_sat_ptr;   // [ngroups] first two-body / first saturating pair of the group (pairs sorted by kind)
+    std::vector<uint32_t> pairw;       // 2 words per pair: kind-specific operand rows (see build), reaction
+    std::vector<uint32_t> slotw;       // 2 words per listed slot, heaviest first within a group: CSC slot, ent4 offset | n4<<24
+    std::vector<uint32_t> ent4;        // 4 words per entry group; entry = pair index | high 16 bits of the coefficient (a double) << 16; padding = +1 x the zero row (index max_pairs)
   } jc;
   std::string error;
 };

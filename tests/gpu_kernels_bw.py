@@ -20,8 +20,9 @@ s_ = torch.cuda.current_stream().cuda_stream
 for name, fn, nbytes in (
     ("K1 rates", lambda: sol.rates_dev(nk, d_kpar.data_ptr(), d_k.data_ptr(), s_), 8.0 * (rb.NPAR + R)),
     ("K2 rhs", lambda: sol.rhs_jac_dev(nk, d_kpar.data_ptr(), d_ky.data_ptr(), d_k.data_ptr(), d_yd.data_ptr(), 0, s_), 8.0 * (R + 2 * NEQ)),
-    ("K3 jac (2 CTAs/SM, 64-cell tiles)", lambda: sol.rhs_jac_dev(nk, d_kpar.data_ptr(), d_ky.data_ptr(), d_k.data_ptr(), 0, d_pd.data_ptr(), s_), 8.0 * (R + NEQ + sol.NNZ)),
-    ("K3 jac (1 CTA/SM, 128-cell tiles)", lambda: (sol.set_option("k3_variant", 4), sol.rhs_jac_dev(nk, d_kpar.data_ptr(), d_ky.data_ptr(), d_k.data_ptr(), 0, d_pd.data_ptr(), s_), sol.set_option("k3_variant", 2)), 8.0 * (R + NEQ + sol.NNZ))):
+    ("K3 jac (pipelined: cp.async rate rows, prefetched slot words; 2 CTAs/SM, 64-cell tiles)", lambda: sol.rhs_jac_dev(nk, d_kpar.data_ptr(), d_ky.data_ptr(), d_k.data_ptr(), 0, d_pd.data_ptr(), s_), 8.0 * (R + NEQ + sol.NNZ)),
+    ("K3 jac (jac_kernel_wide<2,512>)", lambda: (sol.set_option("k3_variant", 2), sol.rhs_jac_dev(nk, d_kpar.data_ptr(), d_ky.data_ptr(), d_k.data_ptr(), 0, d_pd.data_ptr(), s_), sol.set_option("k3_variant", 3)), 8.0 * (R + NEQ + sol.NNZ)),
+    ("K3 jac (jac_kernel_wide<4,1024>)", lambda: (sol.set_option("k3_variant", 4), sol.rhs_jac_dev(nk, d_kpar.data_ptr(), d_ky.data_ptr(), d_k.data_ptr(), 0, d_pd.data_ptr(), s_), sol.set_option("k3_variant", 3)), 8.0 * (R + NEQ + sol.NNZ))):
     for _ in range(3): fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); tt = 0.0
