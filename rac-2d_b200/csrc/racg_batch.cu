@@ -534,6 +534,64 @@ __device__ __forceinline__ DV<CPL> ldv_s(const double* p) {
   return r;
 }
 
+// Phase 2 of jac_kernel_pipe for one warp: slots s, s + NWARP, ... < se of the group.  sbase = the
+// shared-space address of this lane's columns of the derivative buffer; an entry = byte offset of
+// the pair's row (17 bits) | the top 15 bits of its coefficient as a double.  ACCUM: a later chunk of
+// a hub column adds to what an earlier group stored (coherent read, one slot ahead).
+template <int CPL>
+__device__ __forceinline__ void k3_fma_entry(double (&acc)[CPL], uint32_t sbase, uint32_t ev) {
+  const double cf = __hiloint2double((int)(ev & 0xfffe0000u), 0);
+  const uint32_t addr = sbase + (ev & 0x1ffffu);
+#pragma unroll
+  for (int q = 0; q < CPL; q += 2) {
+    double dx, dy;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(dx), "=d"(dy) : "r"(addr + 8 * q));
+    acc[q] += cf * dx; acc[q + 1] += cf * dy;
+  }
+}
+template <int CPL, int NWARP, bool ACCUM>
+__device__ __forceinline__ void k3_gather(uint32_t sbase, const uint2* __restrict__ slotw, const uint4* __restrict__ ent4,
+                                          int s, int se, double* pdc, unsigned ncu, bool ok, uint2 c0, uint2 c1, uint4 e0) {
+  // c0, c1 = the words of slots s and s + NWARP, e0 = the first entry group of slot s: the caller
+  // requested them before the derivative phase
+  const uint2 none = make_uint2(0u, 0u);
+  const double2 z2 = make_double2(0.0, 0.0);
+  double a0[CPL];
+#pragma unroll
+  for (int q = 0; q < CPL; q += 2) {
+    const double2 t = (ACCUM && s < se) ? __ldcg((const double2*)(pdc + (size_t)((unsigned long long)c0.x * ncu)) + (q >> 1)) : z2;
+    a0[q] = t.x; a0[q + 1] = t.y;
+  }
+#pragma unroll 2
+  for (; s < se; s += NWARP) {
+    const uint2 c2 = (s + 2 * NWARP < se) ? __ldg(slotw + s + 2 * NWARP) : none;
+    const uint4 e1 = __ldg(ent4 + (c1.y & 0xffffffu));
+    double a1[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; q += 2) {
+      const double2 t = (ACCUM && s + NWARP < se) ? __ldcg((const double2*)(pdc + (size_t)((unsigned long long)c1.x * ncu)) + (q >> 1)) : z2;
+      a1[q] = t.x; a1[q + 1] = t.y;
+    }
+    const int n4 = (int)(c0.y >> 24);
+    const uint4* const ep = ent4 + (c0.y & 0xffffffu);
+    uint4 e = e0;
+    for (int i4 = 0;;) {
+      k3_fma_entry<CPL>(a0, sbase, e.x); k3_fma_entry<CPL>(a0, sbase, e.y);
+      k3_fma_entry<CPL>(a0, sbase, e.z); k3_fma_entry<CPL>(a0, sbase, e.w);
+      if (++i4 >= n4) break;
+      e = __ldg(ep + i4);
+    }
+    if (ok) {
+      double2* const o = (double2*)(pdc + (size_t)((unsigned long long)c0.x * ncu));
+#pragma unroll
+      for (int q = 0; q < CPL; q += 2) __stcs(o + (q >> 1), make_double2(a0[q], a0[q + 1]));
+    }
+    c0 = c1; c1 = c2; e0 = e1;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) a0[q] = a1[q];
+  }
+}
+
 template <int CPL, int NTH, int PB>
 __global__ void __launch_bounds__(NTH, 1024 / NTH)
 jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double* __restrict__ cellpar,
@@ -556,6 +614,7 @@ jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double
   const uint2* const slotw = (const uint2*)jc.slotw;
   const uint4* const ent4 = (const uint4*)jc.ent4;
   double* const myd = dbuf + CPL * l;                        // this lane's columns of the buffer
+  const uint32_t sbase = smem_u32(myd);
   const double2 z2 = make_double2(0.0, 0.0);
   for (int tile = blockIdx.x; tile * TC < ncell; tile += gridDim.x) {
     const int cell = tile * TC + CPL * l;
@@ -576,22 +635,34 @@ jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double
         for (int q = 0; q < CPL / 2; ++q) __stcs(o + q, z2);
       }
     }
+    uint2 pwl = make_uint2(0u, 0u);
+    {
+      const int q = __ldg(jc.grp_pair_ptr) + w + NWARP * l;
+      if (ng > 0 && q < __ldg(jc.grp_pair_ptr + 1)) pwl = __ldg(pairw + q);
+    }
     for (int g = 0; g < ng; ++g) {
       __syncthreads();                                       // the previous group's gather is done with dbuf (and gp[] is set)
       const int pb = gp[g], pe = gp[g + 1];
-      // ---- 1a: every rate row of the group
-      if (ok) {
-        const double* const rc = rates + cell;
+      // ---- 1a: every rate row of the group.  Lane i of a warp holds the word of the warp's i-th
+      // pair (pwl, requested during the previous group's gather)
+      {
+        const double* const rc = rates + (ok ? cell : 0);
 #pragma unroll 4
-        for (int p = pb + w; p < pe; p += NWARP) {
-          const double* const src = rc + (size_t)((unsigned long long)__ldg(&pairw[p].y) * ncu);
+        for (int p = pb + w, i = 0; p < pe; p += NWARP, ++i) {
+          const double* const src = rc + (size_t)((unsigned long long)__shfl_sync(0xffffffffu, pwl.y, i) * ncu);
           double* const dst = myd + (p - pb) * TC;
+          if (ok) {
 #pragma unroll
-          for (int q = 0; q < CPL; q += 2) cp_async16(dst + q, src + q);
+            for (int q = 0; q < CPL; q += 2) cp_async16(dst + q, src + q);
+          }
         }
       }
       // ---- 1b: derivatives in place (branches of chem_ode_jac, src/disk.f90:4765-4866).  One-body
       // pairs: the derivative is the rate, nothing to do.  Two-body pairs, PB at a time:
+      // the gather phase's first slot words and entry group are requested here, behind the rate rows
+      const int s0 = gs[g] + w, se = gs[g + 1];
+      const uint2 c0 = (s0 < se) ? __ldg(slotw + s0) : make_uint2(0u, 0u);
+      const uint2 c1 = (s0 + NWARP < se) ? __ldg(slotw + s0 + NWARP) : make_uint2(0u, 0u);
       bool landed = false;
       const int p2 = g2[g], p3 = g3[g];
       // (a pair is finished by the warp that requested its rate row: p = pb + w modulo NWARP, so that
@@ -601,7 +672,8 @@ jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double
 #pragma unroll
         for (int u = 0; u < PB; ++u) {
           const int p = p0 + u * NWARP;
-          xw[u] = (p < p3) ? __ldg(&pairw[p].x) : 0u;
+          const uint32_t xs = __shfl_sync(0xffffffffu, pwl.x, ((p - pb) / NWARP) & 31);
+          xw[u] = (p < p3) ? xs : 0u;
           yo[u] = ldv_g<CPL>(yc + (size_t)((unsigned long long)(xw[u] & 1023u) * ncu));
           ys[u] = ldv_g<CPL>(yc + (size_t)((unsigned long long)((xw[u] >> 10) & 1023u) * ncu));
         }
@@ -626,7 +698,7 @@ jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double
       }
       // saturating desorption (a handful per network)
       for (int p = p3 + ((w - (p3 - pb)) & (NWARP - 1)); p < pe; p += NWARP) {
-        const uint32_t x = __ldg(&pairw[p].x);
+        const uint32_t x = __shfl_sync(0xffffffffu, pwl.x, ((p - pb) / NWARP) & 31);
         const DV<CPL> y1 = ldv_g<CPL>(yc + (size_t)((unsigned long long)(x & 1023u) * ncu));
         if (!landed) { cp_async_wait_all(); landed = true; }
         double* const kp = myd + (p - pb) * TC;
@@ -646,57 +718,17 @@ jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double
 #pragma unroll
         for (int q = 0; q < CPL; q += 2) *((double2*)kp + (q >> 1)) = make_double2(d[q], d[q + 1]);
       }
+      const uint4 e0 = __ldg(ent4 + (c0.y & 0xffffffu));
       if (!landed) cp_async_wait_all();
       __syncthreads();
       // ---- 2: gather the listed slots
-      const int se = gs[g + 1];
-      const bool accum = ga[g] != 0 && ok;
-      int s = gs[g] + w;
-      const uint2 none = make_uint2(0u, 0u);
-      uint2 c0 = (s < se) ? __ldg(slotw + s) : none;
-      uint2 c1 = (s + NWARP < se) ? __ldg(slotw + s + NWARP) : none;
-      uint4 e0 = __ldg(ent4 + (c0.y & 0xffffffu));
-      // coherent reads (not the read-only path): an earlier group of this kernel stored the value
-      double a0[CPL];
-#pragma unroll
-      for (int q = 0; q < CPL; q += 2) {
-        const double2 t = accum ? __ldcg((const double2*)(pdc + (size_t)((unsigned long long)c0.x * ncu)) + (q >> 1)) : z2;
-        a0[q] = t.x; a0[q + 1] = t.y;
+      // the pair words of the next group land while this one is gathered
+      {
+        const int q = gp[g + 1] + w + NWARP * l;
+        pwl = (g + 1 < ng && q < gp[g + 2]) ? __ldg(pairw + q) : make_uint2(0u, 0u);
       }
-      for (; s < se; s += NWARP) {
-        const uint2 c2 = (s + 2 * NWARP < se) ? __ldg(slotw + s + 2 * NWARP) : none;
-        const uint4 e1 = __ldg(ent4 + (c1.y & 0xffffffu));
-        double a1[CPL];
-        const bool more = accum && s + NWARP < se;
-#pragma unroll
-        for (int q = 0; q < CPL; q += 2) {
-          const double2 t = more ? __ldcg((const double2*)(pdc + (size_t)((unsigned long long)c1.x * ncu)) + (q >> 1)) : z2;
-          a1[q] = t.x; a1[q + 1] = t.y;
-        }
-        const int n4 = (int)(c0.y >> 24);
-        const uint4* const ep = ent4 + (c0.y & 0xffffffu);
-        uint4 e = e0;
-        for (int i4 = 0;;) {
-          const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const DV<CPL> dv = ldv_s<CPL>(myd + (ev[j] & 0xffffu) * TC);
-            const double cf = __hiloint2double((int)(ev[j] & 0xffff0000u), 0);
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) a0[q] += cf * dv.v[q];
-          }
-          if (++i4 >= n4) break;
-          e = __ldg(ep + i4);
-        }
-        if (ok) {
-          double2* const o = (double2*)(pdc + (size_t)((unsigned long long)c0.x * ncu));
-#pragma unroll
-          for (int q = 0; q < CPL; q += 2) __stcs(o + (q >> 1), make_double2(a0[q], a0[q + 1]));
-        }
-        c0 = c1; c1 = c2; e0 = e1;
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) a0[q] = a1[q];
-      }
+      if (ga[g] != 0 && ok) k3_gather<CPL, NWARP, true>(sbase, slotw, ent4, s0, se, pdc, ncu, ok, c0, c1, e0);
+      else k3_gather<CPL, NWARP, false>(sbase, slotw, ent4, s0, se, pdc, ncu, ok, c0, c1, e0);
     }
   }
 }

@@ -871,8 +871,10 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
       jc.pairw.push_back(x); jc.pairw.push_back(pr & 0xffff);
     }
     // entry of the repacked lists: local pair index | high 16 bits of the coefficient as a double
-    auto cf16 = [](int c) { const double d = (double)c; uint64_t b; memcpy(&b, &d, 8); return (uint32_t)(b >> 48) << 16; };
-    const uint32_t padent = (uint32_t)jc.max_pairs | cf16(1);
+    // (byte offset of the pair's 512-byte row in the 64-cell derivative buffer, 17 bits | top 15 bits of the double)
+    auto cf15 = [](int c) { const double d = (double)c; uint64_t b; memcpy(&b, &d, 8); return (uint32_t)(b >> 49) << 17; };
+    auto ent_of = [&](uint32_t local, int c) { return (local * 512u) | cf15(c); };
+    const uint32_t padent = ent_of((uint32_t)jc.max_pairs, 1);
     for (int g = 0; g < jc.ngroups; ++g) {
       std::vector<std::pair<int, int>> ord;   // (-entries, listed slot)
       for (int s2 = jc.grp_slot_ptr[g]; s2 < jc.grp_slot_ptr[g + 1]; ++s2)
@@ -884,7 +886,7 @@ bool build_host_net(HostNet& hn, int R, int N, const int* reac, const int* prod,
         jc.slotw.push_back((uint32_t)jc.slot_id[s2]);
         jc.slotw.push_back((uint32_t)(jc.ent4.size() / 4) | ((uint32_t)n4 << 24));
         for (int e = e0; e < e0 + 4 * n4; ++e)
-          jc.ent4.push_back(e < e1 ? ((jc.ent[e] & 0xffffu) | cf16((int)(jc.ent[e] >> 24) - 4)) : padent);
+          jc.ent4.push_back(e < e1 ? ent_of(jc.ent[e] & 0xffffffu, (int)(jc.ent[e] >> 24) - 4) : padent);
       }
     }
   }
