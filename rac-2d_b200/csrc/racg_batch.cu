@@ -592,15 +592,16 @@ __device__ __forceinline__ void k3_gather(uint32_t sbase, const uint2* __restric
   }
 }
 
-template <int CPL, int NTH, int PB>
+template <int CPL, int NTH, int PB, int NBUF>
 __global__ void __launch_bounds__(NTH, 1024 / NTH)
 jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double* __restrict__ cellpar,
                 const double* __restrict__ y, const double* __restrict__ rates, double* __restrict__ pd) {
   extern __shared__ __align__(16) double sm[];
   constexpr int TC = 32 * CPL, NWARP = NTH >> 5;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  double* const dbuf = sm;                                   // [max_pairs + 1][TC], the last row = 0
-  int* const gp = (int*)(dbuf + (size_t)(jc.max_pairs + 1) * TC);   // pair_ptr[ng+1] | slot_ptr[ng+1] | accum[ng]
+  double* const dbuf = sm;                                   // NBUF x [max_pairs + 1][TC], the last row of each = 0
+  const int BUFD = (jc.max_pairs + 1) * TC;                  // doubles per buffer
+  int* const gp = (int*)(dbuf + NBUF * (size_t)BUFD);        // pair_ptr[ng+1] | slot_ptr[ng+1] | accum[ng] | ...
   const int ng = jc.ngroups;
   int* const gs = gp + ng + 1;
   int* const ga = gs + ng + 1;
@@ -609,12 +610,10 @@ jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double
   for (int i = threadIdx.x; i <= ng; i += NTH) { gp[i] = __ldg(jc.grp_pair_ptr + i); gs[i] = __ldg(jc.grp_slot_ptr + i); }
   for (int i = threadIdx.x; i < ng; i += NTH) { ga[i] = __ldg(jc.grp_accum + i); g2[i] = __ldg(jc.grp_two_ptr + i); g3[i] = __ldg(jc.grp_sat_ptr + i); }
   const unsigned ncu = (unsigned)ncell;
-  for (int i = threadIdx.x; i < TC; i += NTH) dbuf[(size_t)jc.max_pairs * TC + i] = 0.0;
+  for (int i = threadIdx.x; i < NBUF * TC; i += NTH) dbuf[(size_t)(i / TC) * BUFD + (size_t)jc.max_pairs * TC + (i % TC)] = 0.0;
   const uint2* const pairw = (const uint2*)jc.pairw;
   const uint2* const slotw = (const uint2*)jc.slotw;
   const uint4* const ent4 = (const uint4*)jc.ent4;
-  double* const myd = dbuf + CPL * l;                        // this lane's columns of the buffer
-  const uint32_t sbase = smem_u32(myd);
   const double2 z2 = make_double2(0.0, 0.0);
   for (int tile = blockIdx.x; tile * TC < ncell; tile += gridDim.x) {
     const int cell = tile * TC + CPL * l;
@@ -635,27 +634,42 @@ jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double
         for (int q = 0; q < CPL / 2; ++q) __stcs(o + q, z2);
       }
     }
-    uint2 pwl = make_uint2(0u, 0u);
-    {
-      const int q = __ldg(jc.grp_pair_ptr) + w + NWARP * l;
-      if (ng > 0 && q < __ldg(jc.grp_pair_ptr + 1)) pwl = __ldg(pairw + q);
+    // NBUF = 1: two barriers per group (the buffer is refilled after the gather).  NBUF = 2: group g
+    // lives in buffer g & 1, its rate rows are requested (1a) right after the barrier that ends the
+    // derivative phase of group g - 1, so they travel while that group is gathered, and there is ONE
+    // barrier per group: a warp that finishes its slots early goes on to the next group's
+    // derivatives in the other buffer (last read by the gather of group g - 2, which every warp
+    // finished before that barrier).
+    __syncthreads();                                         // the previous tile is done with the buffers (and gp[] is set)
+    uint2 pwl = make_uint2(0u, 0u);                          // lane i: the word of this warp's i-th pair of the group
+    auto request_rows = [&](int g, uint2 pw) {
+      const int pb = gp[g], pe = gp[g + 1];
+      const double* const rc = rates + (ok ? cell : 0);
+      double* const dcol = dbuf + (NBUF == 2 ? (g & 1) * BUFD : 0) + CPL * l;
+#pragma unroll 4
+      for (int p = pb + w, i = 0; p < pe; p += NWARP, ++i) {
+        const double* const src = rc + (size_t)((unsigned long long)__shfl_sync(0xffffffffu, pw.y, i) * ncu);
+        double* const dst = dcol + (p - pb) * TC;
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < CPL; q += 2) cp_async16(dst + q, src + q);
+        }
+      }
+    };
+    if (ng > 0) {
+      const int q = gp[0] + w + NWARP * l;
+      if (q < gp[1]) pwl = __ldg(pairw + q);
+      request_rows(0, pwl);
     }
     for (int g = 0; g < ng; ++g) {
-      __syncthreads();                                       // the previous group's gather is done with dbuf (and gp[] is set)
       const int pb = gp[g], pe = gp[g + 1];
-      // ---- 1a: every rate row of the group.  Lane i of a warp holds the word of the warp's i-th
-      // pair (pwl, requested during the previous group's gather)
-      {
-        const double* const rc = rates + (ok ? cell : 0);
-#pragma unroll 4
-        for (int p = pb + w, i = 0; p < pe; p += NWARP, ++i) {
-          const double* const src = rc + (size_t)((unsigned long long)__shfl_sync(0xffffffffu, pwl.y, i) * ncu);
-          double* const dst = myd + (p - pb) * TC;
-          if (ok) {
-#pragma unroll
-            for (int q = 0; q < CPL; q += 2) cp_async16(dst + q, src + q);
-          }
-        }
+      double* const myd = dbuf + (NBUF == 2 ? (g & 1) * BUFD : 0) + CPL * l;   // this lane's columns of the group's buffer
+      const uint32_t sbase = smem_u32(myd);
+      // the pair words of the next group: needed after the barrier
+      uint2 pwn = make_uint2(0u, 0u);
+      if (g + 1 < ng) {
+        const int q = gp[g + 1] + w + NWARP * l;
+        if (q < gp[g + 2]) pwn = __ldg(pairw + q);
       }
       // ---- 1b: derivatives in place (branches of chem_ode_jac, src/disk.f90:4765-4866).  One-body
       // pairs: the derivative is the rate, nothing to do.  Two-body pairs, PB at a time:
@@ -722,13 +736,11 @@ jac_kernel_pipe(const DevNet net, const JacColTables jc, int ncell, const double
       if (!landed) cp_async_wait_all();
       __syncthreads();
       // ---- 2: gather the listed slots
-      // the pair words of the next group land while this one is gathered
-      {
-        const int q = gp[g + 1] + w + NWARP * l;
-        pwl = (g + 1 < ng && q < gp[g + 2]) ? __ldg(pairw + q) : make_uint2(0u, 0u);
-      }
+      if (NBUF == 2 && g + 1 < ng) request_rows(g + 1, pwn);
       if (ga[g] != 0 && ok) k3_gather<CPL, NWARP, true>(sbase, slotw, ent4, s0, se, pdc, ncu, ok, c0, c1, e0);
       else k3_gather<CPL, NWARP, false>(sbase, slotw, ent4, s0, se, pdc, ncu, ok, c0, c1, e0);
+      pwl = pwn;
+      if (NBUF == 1 && g + 1 < ng) { __syncthreads(); request_rows(g + 1, pwn); }
     }
   }
 }
@@ -807,14 +819,24 @@ cudaError_t launch_jac(const DevNet& net, const JacColTables& jc, int ncell, con
   const bool aligned = ((size_t)pd % 32) == 0 && ((size_t)y % 32) == 0 && ((size_t)rates % 32) == 0 && ((size_t)cellpar % 32) == 0;
   // two 64-cell CTAs per SM (lane = 2 cells) when their derivative buffers fit side by side
   const size_t smem2 = (size_t)jc.max_pairs * 64 * sizeof(double);
-  // pipelined kernel: two CTAs per SM, 64-cell tiles (lane = 2 cells)
-  const size_t smemp = ((size_t)jc.max_pairs + 1) * 64 * sizeof(double) + (5 * (size_t)jc.ngroups + 2) * sizeof(int);
-  if (g_k3_variant == 3 && ncell % 2 == 0 && aligned && (smemp + 1024) * 2 <= 227 * 1024) {
-    auto kern = jac_kernel_pipe<2, 512, 4>;
-    cudaError_t e3 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp);
+  // pipelined kernel, 64-cell tiles (lane = 2 cells): two 512-thread CTAs per SM with one derivative buffer each
+  // (variant 3, default), or one 1024-thread CTA per SM with two buffers and one barrier per group (variant 5)
+  const size_t smemp1 = ((size_t)jc.max_pairs + 1) * 64 * sizeof(double) + (5 * (size_t)jc.ngroups + 2) * sizeof(int);
+  const size_t smemp2 = smemp1 + ((size_t)jc.max_pairs + 1) * 64 * sizeof(double);
+  if (g_k3_variant == 5 && ncell % 2 == 0 && aligned && smemp2 + 1024 <= 227 * 1024) {
+    auto kern = jac_kernel_pipe<2, 1024, 4, 2>;
+    cudaError_t e3 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp2);
     if (e3 != cudaSuccess) return e3;
     const int ntiles = (ncell + 63) / 64;
-    kern<<<ntiles < 2 * nsm ? ntiles : 2 * nsm, 512, smemp, st>>>(net, jc, ncell, cellpar, y, rates, pd);
+    kern<<<ntiles < nsm ? ntiles : nsm, 1024, smemp2, st>>>(net, jc, ncell, cellpar, y, rates, pd);
+    return cudaGetLastError();
+  }
+  if ((g_k3_variant == 3 || g_k3_variant == 5) && ncell % 2 == 0 && aligned && (smemp1 + 1024) * 2 <= 227 * 1024) {
+    auto kern = jac_kernel_pipe<2, 512, 4, 1>;
+    cudaError_t e3 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp1);
+    if (e3 != cudaSuccess) return e3;
+    const int ntiles = (ncell + 63) / 64;
+    kern<<<ntiles < 2 * nsm ? ntiles : 2 * nsm, 512, smemp1, st>>>(net, jc, ncell, cellpar, y, rates, pd);
     return cudaGetLastError();
   }
   if (g_k3_variant != 4 && ncell % 2 == 0 && aligned && (smem2 + 1024) * 2 <= 227 * 1024) {
