@@ -913,9 +913,113 @@ std::string describe_host_net(const HostNet& hn) {
   return std::string(buf);
 }
 
+// Host emulation of the stand-alone Jacobian kernel's tables (HostNet::JacCols incl. the repacked
+// pairw / slotw / ent4 / kind pointers of jac_kernel_pipe) against a direct evaluation of
+// chem_ode_jac (src/disk.f90:4746-4903, evolT = F) on one pseudo-random state.
+static bool selfcheck_jac_tables(const HostNet& hn, std::string& err) {
+  const HostNet::JacCols& jc = hn.jc;
+  auto fail = [&](const std::string& m) { err = "K3 tables: " + m; return false; };
+  const int R = hn.R, NEQ = hn.NEQ, NNZ = hn.NNZ;
+  if (jc.pairw.size() != 2 * jc.pair.size() || jc.slotw.size() != 2 * jc.slot_id.size() ||
+      (int)jc.grp_two_ptr.size() != jc.ngroups || (int)jc.grp_sat_ptr.size() != jc.ngroups || jc.ent4.size() % 4)
+    return fail("sizes");
+  std::vector<double> k(R), y(NEQ);
+  uint64_t st = 88172645463325252ull;
+  auto rnd = [&] { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+  for (auto& v : k) v = 0.5 + rnd();
+  for (auto& v : y) { v = 0.5 + rnd(); if (rnd() < 0.05) v = -v; }
+  const double DS = 1.7;
+  auto slot_of = [&](int row, int col) -> int {
+    for (int q = hn.ia[col] - 1; q < hn.ia[col + 1] - 1; ++q) if (hn.ja[q] - 1 == row) return q;
+    return -1;
+  };
+  std::vector<double> ref(NNZ, 0.0), scale(NNZ, 0.0), tab(NNZ, 0.0);
+  for (int i = 0; i < R; ++i) {
+    const uint32_t w = hn.fw[i];
+    const int kind = (w >> 20) & 3, r1 = w & 1023, r2 = (w >> 10) & 1023;
+    if (kind == FK_SKIP) continue;
+    std::map<int, int> net;
+    for (int q = 0; q < hn.n_reac[i]; ++q) net[hn.reac[3 * i + q] - 1] -= 1;
+    for (int q = 0; q < hn.n_prod[i]; ++q) net[hn.prod[4 * i + q] - 1] += 1;
+    for (int which = 0; which < 2; ++which) {
+      double d;
+      int col;
+      if (kind == FK_ONE) { if (which) continue; d = k[i]; col = r1; }
+      else if (kind == FK_TWO) {
+        if (which && r2 == r1) continue;
+        d = (r1 != r2) ? (which == 0 ? k[i] * y[r2] : k[i] * y[r1]) : 2.0 * k[i] * y[r2];
+        if (y[r1] < 0.0 && y[r2] < 0.0) d = -d;
+        col = which == 0 ? r1 : r2;
+      } else {
+        if (which) continue;
+        const double tmp2 = DS * hn.sat_c[w >> 22];
+        d = 0.0;
+        if (tmp2 > 0.0) { const double tmp1 = 1.0 / tmp2, tmp = y[r1] * tmp1; d = (tmp <= 1e-4) ? k[i] * tmp1 : k[i] * tmp1 * std::exp(-tmp); }
+        col = r1;
+      }
+      for (auto& kv : net) {
+        if (kv.second == 0) continue;
+        const int sl = slot_of(kv.first, col);
+        if (sl < 0) return fail("a reaction term falls outside the CSC pattern");
+        ref[sl] += kv.second * d; scale[sl] += std::fabs(kv.second * d);
+      }
+    }
+  }
+  std::vector<char> seen(NNZ, 0);
+  std::vector<double> dbuf((size_t)jc.max_pairs + 1, 0.0);
+  for (int g = 0; g < jc.ngroups; ++g) {
+    const int pb = jc.grp_pair_ptr[g], pe = jc.grp_pair_ptr[g + 1], p2 = jc.grp_two_ptr[g], p3 = jc.grp_sat_ptr[g];
+    if (!(pb <= p2 && p2 <= p3 && p3 <= pe) || pe - pb > jc.max_pairs) return fail("group pointers");
+    for (int p = pb; p < pe; ++p) {
+      const uint32_t x = jc.pairw[2 * p], r = jc.pairw[2 * p + 1];
+      if (r != (jc.pair[p] & 0xffffu) || (int)r >= R) return fail("pair word / reaction");
+      const int kind = (hn.fw[r] >> 20) & 3;
+      if (kind != (p < p2 ? FK_ONE : p < p3 ? FK_TWO : FK_SAT)) return fail("pairs are not sorted by kind");
+      double d;
+      if (p < p2) d = k[r];
+      else if (p < p3) {
+        const double yo = y[x & 1023u], ys = y[(x >> 10) & 1023u];
+        d = ((x >> 20) ? 2.0 : 1.0) * k[r] * yo;
+        if (yo < 0.0 && ys < 0.0) d = -d;
+      } else {
+        const double tmp2 = DS * hn.sat_c[x >> 10];
+        d = 0.0;
+        if (tmp2 > 0.0) { const double tmp1 = 1.0 / tmp2, tmp = y[x & 1023u] * tmp1; d = (tmp <= 1e-4) ? k[r] * tmp1 : k[r] * tmp1 * std::exp(-tmp); }
+      }
+      dbuf[p - pb] = d;
+    }
+    for (int q = pe - pb; q < jc.max_pairs; ++q) dbuf[q] = std::nan("");   // stale rows must never be read
+    dbuf[jc.max_pairs] = 0.0;
+    for (int s2 = jc.grp_slot_ptr[g]; s2 < jc.grp_slot_ptr[g + 1]; ++s2) {
+      const uint32_t slot = jc.slotw[2 * s2], off = jc.slotw[2 * s2 + 1] & 0xffffffu, n4 = jc.slotw[2 * s2 + 1] >> 24;
+      if ((int)slot >= NNZ || n4 < 1 || (size_t)4 * (off + n4) > jc.ent4.size()) return fail("slot word");
+      if (!jc.grp_accum[g] && seen[slot]) return fail("a slot is stored twice");
+      if (jc.grp_accum[g] && !seen[slot] && std::find(jc.zero_slots.begin(), jc.zero_slots.end(), (int)slot) == jc.zero_slots.end())
+        return fail("an accumulating chunk meets a slot nobody initialised");
+      double acc = jc.grp_accum[g] ? tab[slot] : 0.0;
+      for (size_t e = (size_t)4 * off; e < (size_t)4 * (off + n4); ++e) {
+        const uint32_t v = jc.ent4[e], byte = v & 0x1ffffu;
+        if (byte % 512u || byte / 512u > (uint32_t)jc.max_pairs) return fail("entry offset");
+        const uint64_t bits = (uint64_t)(v & 0xfffe0000u) << 32;
+        double cf; memcpy(&cf, &bits, 8);
+        acc += cf * dbuf[byte / 512u];
+      }
+      tab[slot] = acc; seen[slot] = 1;
+    }
+  }
+  for (int z : jc.zero_slots) if (z < 0 || z >= NNZ) return fail("zero slot index");
+  for (int q = 0; q < NNZ; ++q) {
+    const bool zero = std::find(jc.zero_slots.begin(), jc.zero_slots.end(), q) != jc.zero_slots.end();
+    if (!seen[q] && !zero) return fail("a CSC slot is neither gathered nor zeroed");
+    if (!(std::fabs(tab[q] - ref[q]) <= 1e-12 * scale[q])) return fail("gathered value differs from the direct evaluation at slot " + std::to_string(q));
+  }
+  return true;
+}
+
 bool selfcheck_schedules(const HostNet& hn, std::string& err) {
   const HostNet::LevelLU& g = hn.glu;
   const HostNet::SolveSched& ss = hn.ss;
+  if (!selfcheck_jac_tables(hn, err)) return false;
   if (g.nlev == 0) { err = "no level-parallel schedule for this network"; return false; }
   const int nh = hn.nh, nt = hn.nt;
   auto fail = [&](const std::string& m) { err = m; return false; };

@@ -126,9 +126,9 @@ def _rel_to_scale(a, b, scale):
 
 @pytest.mark.parametrize("ncell", [70, 71, 132])
 def test_rhs_jac_match_oracle(setupA, ncell):
-    """ncell = 70: even (streaming K2; K3 with two cells per lane, two CTAs per SM), ragged against
-    every tile size; 71: odd (fallback K2 with 4-cell tiles, K3 with one cell per lane); 132: a
-    multiple of 4, also run through the one-CTA-per-SM K3 with four cells per lane."""
+    """ncell = 70: even (streaming K2; pipelined K3 with two cells per lane, two CTAs per SM), ragged
+    against every tile size; 71: odd (fallback K2 with 4-cell tiles, K3 with one cell per lane); 132: a
+    multiple of 4, also run through the one-CTA-per-SM wide K3 with four cells per lane."""
     rb, net, sol, onet, y0s = setupA
     par, y0 = _cells(rb, net, y0s, ncell)
     rng = np.random.default_rng(1)
@@ -142,11 +142,16 @@ def test_rhs_jac_match_oracle(setupA, ncell):
         k[c] = onet.cal_rates(par[c])
     ydot, pd = sol.chem_ode_f_jac(par, y, k)
     assert ydot.shape == (ncell, net.NEQ) and pd.shape == (ncell, sol.NNZ)
-    if ncell % 4 == 0:
-        sol.set_option("k3_variant", 4)
-        _, pd4 = sol.chem_ode_f_jac(par, y, k, want_f=False)
-        sol.set_option("k3_variant", 2)
-        assert np.array_equal(pd4, pd), "the two wide K3 variants add the same terms in the same order"
+    if ncell % 2 == 0:
+        # default = the pipelined K3 (variant 3); 2 / 4 = the wide kernels, 5 = one CTA per SM with two
+        # buffers: every variant adds the same terms in the same order
+        for variant in ((2, 5, 4) if ncell % 4 == 0 else (2, 5)):
+            sol.set_option("k3_variant", variant)
+            try:
+                _, pdv = sol.chem_ode_f_jac(par, y, k, want_f=False)
+            finally:
+                sol.set_option("k3_variant", 3)
+            assert np.array_equal(pdv, pd), f"K3 variant {variant} differs from the default kernel"
     for c in range(ncell):
         fo = onet.ode_f(par[c], k[c], y[c])
         # cancellation makes a relative test against |ydot| meaningless: the rounding scale
