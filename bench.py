@@ -12,6 +12,7 @@ path, the final abundance gather is one NCCL all_gather).
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port)
     python bench.py --network rate12-withGrain               # configs[2] network
     python bench.py --stratified                             # configs[4] stiffness strata
+    python bench.py --andrews                                # configs[3]: emulated ncol=200 Andrews-disk grid
     python bench.py --inlib --gpus N                         # N GPUs through ONE racg_solve_batch
                                                              # call (racg_use_devices), no torchrun
 
@@ -113,6 +114,10 @@ def config_dict(args, R, NEQ, NNZ, synth):
     """identical in both arms (the driver compares them)"""
     which = "configs[4] (stiffness-stratified cells, 4 strata interleaved)" if args.stratified else \
         ("configs[2] network" if args.network == "rate12-withGrain" else "configs[1]")
+    if args.andrews:
+        which = ("configs[3] (ncol=200 Andrews-2009 disk grid of inp/template_configure.dat, all cells of one structure "
+                 "iteration in one batch; HOST-SIDE EMULATION of the Fortran host's grid and per-cell fields, "
+                 "rac-2d_b200/synth.py:andrews_disk_cells)")
     return {"workload": f"{which}: {args.ncell} synthetic cells per GPU, {args.network} (R={R}, NEQ={NEQ}, NNZ={NNZ}), "
                         f"Garrod08 waterice IC, t=1e-8..1e6 yr, RTOL 1e-4 ATOL 1e-30 (policy j=1), mxstep 6000, "
                         f"reset every 50 outputs, evolT=F, max_runtime_allowed={MAX_RUNTIME:g} s "
@@ -125,6 +130,8 @@ def config_dict(args, R, NEQ, NNZ, synth):
 
 
 def make_cells(synth, args, n, first=0):
+    if args.andrews:   # the emulated disk grid is one fixed list of cells (column by column)
+        return np.ascontiguousarray(synth.andrews_disk_cells()[0][first:first + n])
     return synth.stratified_params(n, first_cell=first) if args.stratified else synth.cell_params(n, first_cell=first)
 
 
@@ -204,6 +211,8 @@ def main():
     ap.add_argument("--ncell", type=int, default=10000, help="cells per GPU per step")
     ap.add_argument("--network", default="rate06-withgrain", choices=list(NETWORKS))
     ap.add_argument("--stratified", action="store_true", help="configs[4]: stiffness-stratified cells")
+    ap.add_argument("--andrews", action="store_true",
+                    help="configs[3]: every cell of an emulated ncol=200 Andrews-disk grid in one batch (cells per GPU = grid cells // gpus)")
     ap.add_argument("--inlib", action="store_true",
                     help="drive --gpus N GPUs from this one process through racg_use_devices + racg_solve_batch")
     ap.add_argument("--cpu-cells", type=int, default=0, help="cells in the CPU sample (0 = 8 x cores; 4 x cores per step of --impl reference)")
@@ -213,6 +222,10 @@ def main():
     ap.add_argument("--kernel-ncell", type=int, default=75776,
                     help="cells for the K1-K3 roofline kernels (148 SMs x 128-cell tiles x 4 waves)")
     args = ap.parse_args()
+    if args.andrews:
+        sys.path.insert(0, ROOT)
+        import rac2d_b200.synth as _synth
+        args.ncell = _synth.andrews_disk_cells()[0].shape[0] // max(args.gpus, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -214,3 +214,41 @@ def test_chemical_data_file_has_the_reference_record_layout(rb, tmp_path):
     assert np.array_equal(ab2, ab[:, :ns]) and np.array_equal(cs2, cs) and np.array_equal(ci2, ci)
     rb.write_chemical_data(str(tmp_path), -1, ab, nspecies=ns)
     assert (tmp_path / "chemical_data.bin").stat().st_size == 8 * ncell * ns
+
+
+def test_andrews_disk_emulation_grid():
+    """configs[3] stand-in (rac-2d_b200/synth.py:andrews_disk_cells): 200 columns, the density of
+    src/grid.f90:1741-1818 integrates to the configured disk mass, the refinement rule holds, the
+    fields are finite and inside the ranges the rate routines accept; deterministic."""
+    import rac2d_b200.synth as synth
+    par, geom = synth.andrews_disk_cells()
+    par2, _ = synth.andrews_disk_cells()
+    assert np.array_equal(par, par2)
+    P = synth.P
+    assert len(np.unique(geom[:, 0])) == 200 and 3000 < par.shape[0] < 20000
+    assert abs(geom[:, 0].min() - 0.1) < 1e-12 and abs(geom[:, 1].max() - 200.0) < 1e-9
+    assert np.isfinite(par).all()
+    # mass of the gridded part: both sides of the midplane, mean molecular weight 1.4 per H nucleus
+    r0, r1, z0, z1 = geom.T
+    vol = np.pi * (r1 ** 2 - r0 ** 2) * (z1 - z0) * 2.0 * synth.phy_AU2cm ** 3
+    rc, zc = 0.5 * (r0 + r1), 0.5 * (z0 + z1)
+    mass = (synth.andrews_dens(rc, zc) * vol).sum() * 1.4 * synth.phy_mProton_CGS / synth.phy_Msun_CGS
+    # Md normalises the untapered profile between rin and rout; inside r0_in_exp = 3.5 AU the taper
+    # removes all but 1e-5 of it
+    e = lambda r: np.exp(-(r / 80.0) ** 0.5)
+    expect = 2e-2 * (e(3.5) - e(200.0)) / (e(0.1) - e(200.0))
+    assert abs(mass / expect - 1.0) < 0.03, (mass, expect)
+    # refinement: the analytic density varies by <= 1.5 (+ the size clamps) across a cell's height
+    ratio = synth.andrews_dens(rc, z0) / np.maximum(synth.andrews_dens(rc, z1), 1e-300)
+    free = ((z1 - z0) > 0.0201) & (z1 < 199.9)
+    assert np.all(ratio[free] <= 1.5 * (1 + 1e-9))
+    # columns inner -> outer, each from the surface down to the midplane
+    assert np.all(np.diff(geom[:, 0]) >= 0)
+    same = np.diff(geom[:, 0]) == 0
+    assert np.all(np.diff(geom[:, 2])[same] < 0)
+    n, Tg, Td = par[:, P["n_gas"]], par[:, P["Tgas"]], par[:, P["Tdust"]]
+    assert n.min() >= 1e3 and 8 <= Tg.min() and Tg.max() <= 3000 and 5 <= Td.min() and Td.max() <= 1500
+    for k in ("fss_toISM_H2", "fss_toStar_H2", "fss_toISM_CO", "fss_toStar_CO"):
+        assert np.all((par[:, P[k]] > 0) & (par[:, P[k]] <= 1))
+    # Av grows downward inside a column
+    assert np.all(np.diff(par[:, P["Av_toISM"]])[same] > 0)
