@@ -160,17 +160,32 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
                :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 constexpr int K2_TC = 32;          // cells per tile
+// Round-2 additions (ncu: the flux phase and the run lists were stalled on dependent global loads):
+//   * the warp's flux words of a chunk are held one per lane (reaction f0 + w + 32 t in lane t),
+//     requested a chunk ahead and broadcast by shuffle, so the abundance loads of a batch issue at once;
+//   * the warp's run list of the chunk (headers + entry groups, contiguous in rc.stream) is copied
+//     into a private shared-memory slice with cp.async before the flux phase and read from there
+//     (the first `capl` 16-byte groups; the rest of a very long hub list still comes from L2);
+//   * the per-(warp, chunk) offsets / counts and the chunk's list bounds sit in shared memory.
 template <int SPW>
 __global__ void __launch_bounds__(1024, 1)
 rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant__ CUtensorMap rates_map, int ncell,
-                  int nstage, const double* __restrict__ cellpar, const double* __restrict__ y,
+                  int nstage, int capl, const double* __restrict__ cellpar, const double* __restrict__ y,
                   double* __restrict__ ydot) {
   extern __shared__ __align__(128) unsigned char smb[];
   const int NEQ = net.NEQ, RC = rc.RC, nchunk = rc.nchunk;
   const int STG = (RC + 1) * 256;                        // bytes per stage: RC rows + one zero row
   unsigned char* const kb0 = smb;
   uint64_t* const bars = (uint64_t*)(kb0 + (size_t)nstage * STG);
+  int* const meta = (int*)(bars + 8);                    // [32 warps][nchunk][2]: list offset (words), nrun | len4 << 8
+  int* const flo = meta + 64 * nchunk;                   // [nchunk][4]: bounds of the chunk's ONE / TWO / SAT flux lists
+  uint4* const lists = (uint4*)(((uintptr_t)(flo + 4 * nchunk) + 15) & ~(uintptr_t)15);   // [32][capl]
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int ntile = (ncell + 31) >> 5;
   const int my_tiles = (ntile > (int)blockIdx.x) ? (ntile - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -180,7 +195,15 @@ rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 32) for (int s2 = 0; s2 < nstage; ++s2) ((double*)(kb0 + (size_t)s2 * STG))[RC * 32 + tid] = 0.0;
+  for (int i = tid; i < 32 * nchunk; i += 1024) {
+    meta[2 * i] = (int)__ldg(rc.off + i);
+    meta[2 * i + 1] = __ldg(rc.nrun + i) | (__ldg(rc.len4 + i) << 8);
+  }
+  for (int i = tid; i < 4 * nchunk; i += 1024) flo[i] = __ldg(rc.fl_off + i);
   __syncthreads();
+  const int* const mymeta = meta + 2 * w * nchunk;
+  uint4* const mylist = lists + (size_t)w * capl;
+  const uint4* const stream4 = (const uint4*)rc.stream;
   // producer (thread 0): chunk g of this CTA's stream -> stage g % nstage, RC/128 TMA boxes of 128 x 32
   auto issue = [&](int g) {
     const int ti = g / nchunk, c = g - ti * nchunk;
@@ -191,6 +214,12 @@ rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant_
       tma_load_2d(kb0 + (size_t)s2 * STG + (size_t)b * 128 * 256, &rates_map, cell0, c * RC + b * 128, bars + s2);
   };
   if (tid == 0) for (int g = 0; g < nstage - 1 && g < G; ++g) issue(g);
+  // flux word of this lane for chunk c: reaction f0 + w + 32 * lane of the chunk's list
+  auto flux_word = [&](int c) -> uint32_t {
+    const int i = flo[4 * c] + w + 32 * lane;
+    return (i < flo[4 * c + 3]) ? __ldg(rc.flux + i) : 0u;
+  };
+  uint32_t fw_next = (my_tiles > 0) ? flux_word(0) : 0u;
   for (int ti = 0; ti < my_tiles; ++ti) {
     const int cell0 = ((int)blockIdx.x + ti * (int)gridDim.x) * 32;
     const int cell = cell0 + lane;
@@ -198,6 +227,7 @@ rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant_
     const double* const yc = y + (ok ? cell : 0);          // this lane's column of y
     const double DS = ok ? cellpar[(size_t)RACG_P_ratioDust2HnucNum * ncell + cell] *
                            cellpar[(size_t)RACG_P_SitesPerGrain * ncell + cell] : 1.0;
+    const unsigned ncu = (unsigned)ncell;
     double acc[SPW];
 #pragma unroll
     for (int k = 0; k < SPW; ++k) acc[k] = 0.0;
@@ -208,54 +238,67 @@ rhs_stream_kernel(const DevNet net, const RhsChunkDev rc, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         issue(g + nstage - 1);
       }
+      // this chunk's flux words are here; the next chunk's are requested now
+      const uint32_t fw_cur = fw_next;
+      fw_next = flux_word(c + 1 < nchunk ? c + 1 : 0);
+      // the warp's run list of the chunk -> its shared-memory slice
+      const int loff4 = mymeta[2 * c] >> 2, nr = mymeta[2 * c + 1] & 255, len4 = mymeta[2 * c + 1] >> 8;
+      {
+        const int ncopy = len4 < capl ? len4 : capl;
+        for (int i = lane; i < ncopy; i += 32) cp_async16(mylist + i, stream4 + loff4 + i);
+      }
       mbar_wait(bars + s2, (uint32_t)((g / nstage) & 1));
       unsigned char* const kbb = kb0 + (size_t)s2 * STG + lane * 8;     // this lane's column of the stage
       // ---- fluxes in place (branches of chem_ode_f, src/disk.f90:4583-4643), one reaction per warp
       {
-        const int f0 = __ldg(rc.fl_off + 4 * c), f1 = __ldg(rc.fl_off + 4 * c + 1), f2 = __ldg(rc.fl_off + 4 * c + 2),
-                  f3 = __ldg(rc.fl_off + 4 * c + 3);
+        const int f0 = flo[4 * c], f1 = flo[4 * c + 1], f2 = flo[4 * c + 2], f3 = flo[4 * c + 3];
+        const int base = f0 + w;
+        auto first_t = [&](int a) { const int d = a - base; return d > 0 ? (d + 31) >> 5 : 0; };
 #pragma unroll 4
-        for (int i = f0 + w; i < f1; i += 32) {              // k * y1
-          const uint32_t v = __ldg(rc.flux + i);
+        for (int t = 0; base + 32 * t < f1; ++t) {           // k * y1
+          const uint32_t v = __shfl_sync(0xffffffffu, fw_cur, t);
           double* kp = (double*)(kbb + (v & 511u) * 256);
-          *kp = *kp * __ldg(yc + (size_t)((v >> 9) & 1023u) * ncell);
+          *kp = *kp * __ldg(yc + (size_t)((unsigned long long)((v >> 9) & 1023u) * ncu));
         }
 #pragma unroll 4
-        for (int i = f1 + w; i < f2; i += 32) {              // k * y1 * y2, sign as the reference
-          const uint32_t v = __ldg(rc.flux + i);
+        for (int t = first_t(f1); base + 32 * t < f2; ++t) { // k * y1 * y2, sign as the reference
+          const uint32_t v = __shfl_sync(0xffffffffu, fw_cur, t);
           double* kp = (double*)(kbb + (v & 511u) * 256);
-          const double y1 = __ldg(yc + (size_t)((v >> 9) & 1023u) * ncell), y2 = __ldg(yc + (size_t)(v >> 19) * ncell);
+          const double y1 = __ldg(yc + (size_t)((unsigned long long)((v >> 9) & 1023u) * ncu));
+          const double y2 = __ldg(yc + (size_t)((unsigned long long)(v >> 19) * ncu));
           double f = *kp * y1 * y2;
           if (y1 < 0.0 && y2 < 0.0) f = -f;
           *kp = f;
         }
-        for (int i = f2 + w; i < f3; i += 32) {              // saturating desorption
-          const uint32_t v = __ldg(rc.flux + i);
+        for (int t = first_t(f2); base + 32 * t < f3; ++t) { // saturating desorption
+          const uint32_t v = __shfl_sync(0xffffffffu, fw_cur, t);
           double* kp = (double*)(kbb + (v & 511u) * 256);
-          const double k = *kp, y1 = __ldg(yc + (size_t)((v >> 9) & 1023u) * ncell);
+          const double k = *kp, y1 = __ldg(yc + (size_t)((unsigned long long)((v >> 9) & 1023u) * ncu));
           const double tmp1 = DS * net.sat_c[v >> 19];
           double f = k;
           if (tmp1 > 0.0) { const double tmp = y1 / tmp1; f = (tmp <= 1e-4) ? k * tmp : k * (1.0 - exp(-tmp)); }
           *kp = f;
         }
       }
+      cp_async_wait_all();
       __syncthreads();
-      // ---- this warp's species: run lists of the chunk
+      // ---- this warp's species: run lists of the chunk (headers, then the entry groups)
       {
-        const uint32_t* p = rc.stream + __ldg(rc.off + w * nchunk + c);
-        const int nr = __ldg(rc.nrun + w * nchunk + c);
-        const uint4* ep = (const uint4*)(p + ((nr + 3) & ~3));        // entries follow the padded headers
+        const uint32_t* const hp = (const uint32_t*)mylist;
+        const uint4* const gl = stream4 + loff4;
+        int j = (nr + 3) >> 2;                               // entry groups follow the padded headers
+        auto group = [&](int jj) -> uint4 { return jj < capl ? mylist[jj] : __ldg(gl + jj); };
         for (int q = 0; q < nr; ++q) {
-          const uint32_t h = __ldg(p + q);
+          const uint32_t h = hp[q];
           const int k = h & 31, nm = (h >> 5) & 0x1fff, np = h >> 18;
           double a = 0.0;
           for (int i = 0; i < nm; ++i) {
-            const uint4 e = __ldg(ep++);
+            const uint4 e = group(j++);
             a -= *(const double*)(kbb + e.x); a -= *(const double*)(kbb + e.y);
             a -= *(const double*)(kbb + e.z); a -= *(const double*)(kbb + e.w);
           }
           for (int i = 0; i < np; ++i) {
-            const uint4 e = __ldg(ep++);
+            const uint4 e = group(j++);
             a += *(const double*)(kbb + e.x); a += *(const double*)(kbb + e.y);
             a += *(const double*)(kbb + e.z); a += *(const double*)(kbb + e.w);
           }
@@ -515,10 +558,6 @@ jac_kernel_wide(const DevNet net, const JacColTables jc, int ncell, const double
 // CPL = 4 halves the per-pair / per-slot / per-entry instruction overhead per cell against CPL = 2
 // (measured with ncu: the CPL = 2 form issues 3.0 G warp-instructions for 75 776 cells and is
 // issue-bound at 36 % of the HBM peak).  The group pointers sit in shared memory behind the buffer.
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int CPL>
 __device__ __forceinline__ DV<CPL> ldv_g(const double* p) {
   DV<CPL> r;
@@ -785,19 +824,23 @@ cudaError_t launch_rhs(const DevNet& net, const RhsChunkDev& rc, int ncell, cons
     const size_t stg = (size_t)(rc.RC + 1) * 256;
     const int nstage = 2;
     CUtensorMap map;
-    if (nstage * stg + 64 <= 227 * 1024 && make_rates_map(&map, rates, net.R, ncell)) {
-      const size_t smem2 = nstage * stg + 64;
+    // behind the stages: 8 mbarrier slots, the per-(warp, chunk) list words, the chunk bounds, the list slices
+    const size_t fixed = nstage * stg + 64 + (size_t)(64 + 4) * rc.nchunk * sizeof(int) + 16;
+    if (fixed + 32 * 16 * 8 <= 227 * 1024 && make_rates_map(&map, rates, net.R, ncell)) {
+      int capl = (int)((227 * 1024 - fixed) / (32 * 16));
+      if (capl > rc.max_len4) capl = rc.max_len4 > 0 ? rc.max_len4 : 1;
+      const size_t smem2 = fixed + (size_t)capl * 32 * 16;
       const int ntile = (ncell + K2_TC - 1) / K2_TC;
       const int grid = ntile < nsm ? ntile : nsm;
       cudaError_t e2;
       if (rc.spw <= 16) {
         e2 = cudaFuncSetAttribute(rhs_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e2 != cudaSuccess) return e2;
-        rhs_stream_kernel<16><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
+        rhs_stream_kernel<16><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, capl, cellpar, y, ydot);
       } else {
         e2 = cudaFuncSetAttribute(rhs_stream_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e2 != cudaSuccess) return e2;
-        rhs_stream_kernel<24><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, cellpar, y, ydot);
+        rhs_stream_kernel<24><<<grid, 1024, smem2, st>>>(net, rc, map, ncell, nstage, capl, cellpar, y, ydot);
       }
       return cudaGetLastError();
     }

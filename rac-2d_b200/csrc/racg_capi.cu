@@ -264,10 +264,11 @@ static int create_ctx(racg_handle* h, int device, DevCtx** out) {
   {
     RhsChunkDev& r = c->rhsc;
     const HostNet::RhsChunks& s = hn.rhsc;
-    r.RC = s.RC; r.nchunk = s.nchunk; r.spw = s.spw;
+    r.RC = s.RC; r.nchunk = s.nchunk; r.spw = s.spw; r.max_len4 = s.max_len4;
     if ((rc = upload(c, s.slot_species, &r.slot_species))) return rc;
     if ((rc = upload(c, s.off, &r.off))) return rc;
     if ((rc = upload(c, s.nrun, &r.nrun))) return rc;
+    if ((rc = upload(c, s.len4, &r.len4))) return rc;
     if ((rc = upload(c, s.stream, &r.stream))) return rc;
     if ((rc = upload(c, s.fl_off, &r.fl_off))) return rc;
     if ((rc = upload(c, s.flux, &r.flux))) return rc;

@@ -126,8 +126,8 @@ struct BatchArgs {
 
 // streaming K2 schedule (HostNet::RhsChunks)
 struct RhsChunkDev {
-  int RC, nchunk, spw;
-  const int* slot_species; const uint32_t* off; const int* nrun; const uint32_t* stream;
+  int RC, nchunk, spw, max_len4;
+  const int* slot_species; const uint32_t* off; const int* nrun; const int* len4; const uint32_t* stream;
   const int* fl_off; const uint32_t* flux;
 };
 

@@ -153,6 +153,8 @@ struct HostNet {
     std::vector<int> slot_species;      // [nwarp*spw] species id or -1
     std::vector<uint32_t> off;          // [nwarp*nchunk] offset of the run list in stream (multiple of 4)
     std::vector<int> nrun;              // [nwarp*nchunk]
+    std::vector<int> len4;              // [nwarp*nchunk] length of the list (headers + entries) in 16-byte groups
+    int max_len4 = 0;
     std::vector<uint32_t> stream;
     std::vector<int> fl_off;            // [nchunk*4] start of the ONE / TWO / SAT lists of the chunk, end
     std::vector<uint32_t> flux;

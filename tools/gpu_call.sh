@@ -1,5 +1,5 @@
 mkdir -p gpurun_out/r2
-timeout 900 python bench.py --andrews --steps 2 --warmup 3 > gpurun_out/r2/bench_andrews.json 2> gpurun_out/r2/bench_andrews.err; echo "bench rc=$?"
-head -c 300 gpurun_out/r2/bench_andrews.json; tail -3 gpurun_out/r2/bench_andrews.err
-timeout 600 python bench.py --impl reference --andrews --steps 2 --warmup 1 > gpurun_out/r2/bench_andrews_ref.json 2> gpurun_out/r2/bench_andrews_ref.err; echo "ref rc=$?"
-head -c 300 gpurun_out/r2/bench_andrews_ref.json
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "rhs_jac" > gpurun_out/r2/pytest_k2_48.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/r2/pytest_k2_48.log
+timeout 300 python tests/gpu_kernels_bw.py > gpurun_out/r2/kernels_bw_48.log 2>&1; echo "bw rc=$?"
+grep "K2\|K3 jac (pipelined:" gpurun_out/r2/kernels_bw_48.log
