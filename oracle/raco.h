@@ -122,7 +122,8 @@ typedef struct raco_solve_opts {
  * c_solve*n_solve + c_step*NST with per-operation costs of the reference algorithm on one
  * host core, scaled by network size: c_f = 1.04e-8*R, c_jac = 6.45e-9*NEQ*R (column-wise
  * chem_ode_jac), c_lu = 1.41e-7*NNZ, c_solve = 3.0e-9*NNZ, c_step = 6.4e-8*NEQ (fitted to this
- * oracle, jac_mode = 1, -O2, 300 cells of the config-2 stream).  coef[5]. */
+ * oracle, jac_mode = 1, built -O2, 300 cells of the config-2 stream; the constants are
+ * part of the model and do not follow the build flags).  coef[5]. */
 void raco_model_runtime_coefs(int R, int NEQ, int NNZ, double* coef);
 
 /* stats[0..15]: NST,NFE,NJE,NLU,NQU(last),n_solve,n_err,n_restart,n_cfail,n_efail,
